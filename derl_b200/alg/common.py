@@ -1,0 +1,114 @@
+"""Loss / Trainer / Alg: the consumer side of the hot path (reference: derl/alg/common.py —
+r_squared :9-12, total_norm :15-20, Loss :23-45, Trainer :48-78, Alg :81-106).
+
+One addition: `Trainer(grad_sync=...)`, a callable run between `loss.backward()` and the
+gradient clipping (reference :70 / :71) — the insertion point of the NCCL gradient
+all-reduce when the rollout is sharded along the env axis (derl_b200.parallel).
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import summary
+
+
+def r_squared(targets, predictions):
+  """Coefficient of determination with torch's Bessel-corrected std (reference :9-12)."""
+  variance = torch.pow(predictions.std(), 2)
+  return 1. - torch.mean(torch.pow(predictions - targets, 2)) / variance
+
+
+def total_norm(tensors, norm_type=2):
+  """Norm of the tensors as if concatenated into one vector."""
+  if norm_type == float("inf"):
+    return max(t.abs().max() for t in tensors)
+  return sum(t.norm(norm_type) ** norm_type for t in tensors) ** (1. / norm_type)
+
+
+class Loss(ABC):
+  """Algorithm loss function bound to a model."""
+
+  def __init__(self, model, name=None):
+    self.model = model
+    if name is None:
+      name = self.__class__.__name__
+      name = name[:-len("Loss")] if name.endswith("Loss") else name
+      name = name.lower()
+    self.name = name
+    self.call_count = 0
+
+  @property
+  def device(self):
+    return next(self.model.parameters()).device
+
+  def torch_from_numpy(self, arr):
+    """NumPy array (or tensor) -> tensor on the model's device."""
+    if isinstance(arr, torch.Tensor):
+      return arr if arr.device == self.device else arr.to(self.device)
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device=self.device)
+
+  @abstractmethod
+  def __call__(self, data):
+    """Computes and returns loss value on given data."""
+
+
+class Trainer:
+  """loss -> zero_grad -> backward -> [grad_sync] -> clip -> anneal -> optimizer.step."""
+
+  def __init__(self, optimizer, anneals=None, max_grad_norm=None, grad_sync=None):
+    self.optimizer = optimizer
+    self.anneals = anneals or []
+    self.max_grad_norm = max_grad_norm
+    self.grad_sync = grad_sync
+    self.step_count = 0
+
+  def preprocess_gradients(self, parameters, tag):
+    grad_norm = None
+    parameters = list(parameters)
+    if self.max_grad_norm is not None:
+      grad_norm = torch.nn.utils.clip_grad_norm_(parameters, self.max_grad_norm)
+    if summary.should_record():
+      if grad_norm is None:
+        grad_norm = total_norm(p.grad for p in parameters if p.grad is not None)
+      summary.add_scalar(tag, grad_norm, global_step=self.step_count)
+
+  def step(self, alg, data):
+    loss = alg.loss(data)
+    # a flat gradient buffer (grad_sync) must keep its views alive: zero in place then
+    self.optimizer.zero_grad(set_to_none=self.grad_sync is None)
+    loss.backward()
+    if self.grad_sync is not None:
+      self.grad_sync(alg.model)
+    self.preprocess_gradients(alg.model.parameters(), f"{alg.name}/grad_norm")
+    for anneal in self.anneals:
+      if summary.should_record():
+        anneal.summarize(alg.runner.step_count)
+      anneal.step_to(alg.runner.step_count)
+    self.optimizer.step()
+    self.step_count += 1
+    return loss
+
+
+class Alg:
+  """Generic learning algorithm specified by its loss function."""
+
+  def __init__(self, runner, trainer, loss_fn, name=None):
+    self.runner = runner
+    self.model = self.runner.policy.model
+    self.trainer = trainer
+    self.loss_fn = loss_fn
+    self.name = name if name is not None else self.__class__.__name__.lower()
+
+  def loss(self, data):
+    return self.loss_fn(data)
+
+  def step(self, data):
+    return self.trainer.step(self, data)
+
+  def learn(self):
+    from tqdm import tqdm
+    with tqdm(total=len(self.runner)) as pbar:
+      for data in self.runner.run():
+        pbar.update(self.runner.step_count - pbar.n)
+        self.step(data)

@@ -1,0 +1,469 @@
+// K1 — GAE / returns: reverse scan over T, one lane per environment.
+//
+// Arithmetic contract (bit-exact with the reference's NumPy evaluation,
+// derl/runners/trajectory_transforms.py:45-63; scalar-order statement in SURVEY.md §8a):
+//   c_t = reset_t ? 0.0 : gamma            (float64; (1 - reset) * gamma, :57,:59)
+//   k_t = reset_t ? 0.0 : gamma * lambda   (float64; ... * lambda, :62)
+//   A[T-1] = F( F(r - v) + c * last_value )                       (:46 then :53)
+//   A[t]   = F( ((r[t] + c_t * v[t+1]) - v[t]) + k_t * A[t+1] )   (:58-62)
+//   VT[t]  = A[t] +_f32 v[t]                                      (:63)
+// F = round-to-nearest float32; every other operation is an IEEE float64 add/mul issued
+// through __dadd_rn/__dmul_rn so ptxas can never contract them into DFMA.
+//
+// Two variants compute identical bits:
+//   DIRECT  any shape; register double-buffered coalesced global loads.
+//   TMA     N % 16 == 0; each warp owns a 32-env strip, [TT x 32] tiles of rewards /
+//           values / resets are staged through shared memory by cp.async.bulk.tensor
+//           with an mbarrier ring, outputs leave through TMA stores.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace derl {
+namespace {
+
+// ------------------------------------------------------------------ per-step arithmetic
+template <typename RT>
+__device__ __forceinline__ float gae_last_row(RT r, float v, unsigned reset, float last_value,
+                                              double gamma) {
+  float base;
+  if constexpr (std::is_same<RT, double>::value) {
+    base = __double2float_rn(__dsub_rn(r, (double)v));
+  } else {
+    base = __fsub_rn(r, v);
+  }
+  const double c = reset ? 0.0 : gamma;
+  return __double2float_rn(__dadd_rn((double)base, __dmul_rn(c, (double)last_value)));
+}
+
+template <typename RT>
+__device__ __forceinline__ float gae_row(RT r, float v, float v_next, float a_next,
+                                         unsigned reset, double gamma, double gamma_lambda) {
+  const double c = reset ? 0.0 : gamma;
+  const double k = reset ? 0.0 : gamma_lambda;
+  const double delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn(c, (double)v_next)), (double)v);
+  return __double2float_rn(__dadd_rn(delta, __dmul_rn(k, (double)a_next)));
+}
+
+// Block partial -> workspace -> last block writes {sum, sumsq, count}.
+__device__ __forceinline__ void finish_stats(double s1, double s2, double count,
+                                             void* workspace, double* stats, double* scratch,
+                                             int* flag) {
+  double v[2] = {s1, s2};
+  block_sum<2>(v, scratch);
+  if (publish_partials<2>(v, workspace, flag)) {
+    double tot[2];
+    final_sum<2>(tot, workspace, scratch);
+    if (threadIdx.x == 0) {
+      stats[0] = tot[0];
+      stats[1] = tot[1];
+      stats[2] = count;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ DIRECT variant
+template <typename RT, int U>
+__global__ void __launch_bounds__(128)
+gae_direct_kernel(const RT* __restrict__ rewards, const float* __restrict__ values,
+                  const uint8_t* __restrict__ resets, const float* __restrict__ last_value,
+                  long long T, long long N, double gamma, double gamma_lambda,
+                  float* __restrict__ adv, float* __restrict__ vt, void* workspace,
+                  double* stats) {
+  __shared__ double scratch[2 * 32];
+  __shared__ int flag;
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (n < N) {
+    const long long nchunks = (T + U - 1) / U;
+    RT r_cur[U], r_nxt[U];
+    float v_cur[U], v_nxt[U];
+    uint8_t z_cur[U], z_nxt[U];
+    {  // top chunk, possibly partial
+      const long long t0 = (nchunks - 1) * U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long t = t0 + u;
+        const bool ok = t < T;
+        const long long i = ok ? t * N + n : n;
+        r_cur[u] = __ldg(rewards + i);
+        v_cur[u] = __ldg(values + i);
+        z_cur[u] = __ldg(resets + i);
+      }
+    }
+    float v_next = __ldg(last_value + n);
+    float a_next = 0.f;
+    for (long long c = nchunks - 1; c >= 0; --c) {
+      const long long t0 = c * U;
+      if (c > 0) {  // prefetch the chunk below while this one is scanned
+        const long long p0 = t0 - U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = (p0 + u) * N + n;
+          r_nxt[u] = __ldg(rewards + i);
+          v_nxt[u] = __ldg(values + i);
+          z_nxt[u] = __ldg(resets + i);
+        }
+      }
+#pragma unroll
+      for (int u = U - 1; u >= 0; --u) {
+        const long long t = t0 + u;
+        if (t < T) {
+          const float v = v_cur[u];
+          const float a = (t == T - 1)
+                              ? gae_last_row<RT>(r_cur[u], v, z_cur[u], v_next, gamma)
+                              : gae_row<RT>(r_cur[u], v, v_next, a_next, z_cur[u], gamma,
+                                            gamma_lambda);
+          adv[t * N + n] = a;
+          vt[t * N + n] = __fadd_rn(a, v);
+          s1 += (double)a;
+          s2 += (double)a * (double)a;
+          a_next = a;
+          v_next = v;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        r_cur[u] = r_nxt[u];
+        v_cur[u] = v_nxt[u];
+        z_cur[u] = z_nxt[u];
+      }
+    }
+  }
+  if (stats != nullptr) {
+    finish_stats(s1, s2, (double)T * (double)N, workspace, stats, scratch, &flag);
+  }
+}
+
+// ------------------------------------------------------------------ TMA variant
+constexpr int kStripW = 32;  // envs per warp strip == lanes
+
+template <typename RT, int TT, int S>
+struct GaeTmaSmem {
+  static constexpr int kTile = TT * kStripW;
+  static constexpr size_t r_off = 0;
+  static constexpr size_t v_off = r_off + sizeof(RT) * S * kTile;
+  static constexpr size_t a_off = v_off + sizeof(float) * S * kTile;
+  static constexpr size_t vt_off = a_off + sizeof(float) * 2 * kTile;
+  static constexpr size_t z_off = vt_off + sizeof(float) * 2 * kTile;
+  static constexpr size_t bar_off = z_off + (size_t)S * kTile;
+  static constexpr size_t bytes = bar_off + 8 * S;
+  static constexpr uint32_t stage_tx = kTile * (sizeof(RT) + sizeof(float) + 1);
+};
+
+template <typename RT, int TT, int S>
+__global__ void __launch_bounds__(kStripW)
+gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
+               const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_a,
+               const __grid_constant__ CUtensorMap tm_vt, const float* __restrict__ last_value,
+               int T, int N, double gamma, double gamma_lambda, void* workspace, double* stats) {
+  using L = GaeTmaSmem<RT, TT, S>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  RT* sr = reinterpret_cast<RT*>(smem + L::r_off);
+  float* sv = reinterpret_cast<float*>(smem + L::v_off);
+  float* sa = reinterpret_cast<float*>(smem + L::a_off);
+  float* svt = reinterpret_cast<float*>(smem + L::vt_off);
+  uint8_t* sz = smem + L::z_off;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  __shared__ double scratch[2 * 32];
+  __shared__ int flag;
+
+  const int lane = threadIdx.x;
+  const int n0 = blockIdx.x * kStripW;
+  const int n = n0 + lane;
+  const int nchunks = (T + TT - 1) / TT;
+
+  if (lane == 0) {
+    tma_prefetch_desc(&tm_r);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_z);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_vt);
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  auto issue = [&](int chunk, int s) {
+    mbar_expect_tx(&full[s], L::stage_tx);
+    tma_load_2d(sr + (size_t)s * L::kTile, &tm_r, n0, chunk * TT, &full[s]);
+    tma_load_2d(sv + (size_t)s * L::kTile, &tm_v, n0, chunk * TT, &full[s]);
+    tma_load_2d(sz + (size_t)s * L::kTile, &tm_z, n0, chunk * TT, &full[s]);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < S && i < nchunks; ++i) issue(nchunks - 1 - i, i);
+  }
+
+  float v_next = n < N ? __ldg(last_value + n) : 0.f;
+  float a_next = 0.f;
+  double s1 = 0.0, s2 = 0.0;
+
+  for (int i = 0; i < nchunks; ++i) {
+    const int c = nchunks - 1 - i;
+    const int s = i % S;
+    const int o = i & 1;
+    mbar_wait(&full[s], (uint32_t)((i / S) & 1));
+    const RT* r_t = sr + (size_t)s * L::kTile + lane;
+    const float* v_t = sv + (size_t)s * L::kTile + lane;
+    const uint8_t* z_t = sz + (size_t)s * L::kTile + lane;
+    float* a_t = sa + (size_t)o * L::kTile + lane;
+    float* vt_t = svt + (size_t)o * L::kTile + lane;
+    const int t0 = c * TT;
+#pragma unroll
+    for (int tt = TT - 1; tt >= 0; --tt) {
+      const int t = t0 + tt;
+      if (t < T) {  // warp-uniform; false only in the top chunk
+        const RT r = r_t[tt * kStripW];
+        const float v = v_t[tt * kStripW];
+        const unsigned z = z_t[tt * kStripW];
+        const float a = (t == T - 1) ? gae_last_row<RT>(r, v, z, v_next, gamma)
+                                     : gae_row<RT>(r, v, v_next, a_next, z, gamma, gamma_lambda);
+        a_t[tt * kStripW] = a;
+        vt_t[tt * kStripW] = __fadd_rn(a, v);
+        if (n < N) {
+          s1 += (double)a;
+          s2 += (double)a * (double)a;
+        }
+        a_next = a;
+        v_next = v;
+      }
+    }
+    __syncwarp();  // every lane is done reading stage s and writing out-buffer o
+    if (lane == 0) {
+      fence_proxy_async_smem();
+      tma_store_2d(&tm_a, sa + (size_t)o * L::kTile, n0, t0);
+      tma_store_2d(&tm_vt, svt + (size_t)o * L::kTile, n0, t0);
+      bulk_commit();
+      if (i + S < nchunks) issue(c - S, s);
+      bulk_wait_read<1>();  // the store before this one has left smem: buffer o^1 is free
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait<0>();
+  if (stats != nullptr) {
+    finish_stats(s1, s2, (double)T * (double)N, workspace, stats, scratch, &flag);
+  }
+}
+
+// ------------------------------------------------------------------ tensor-map encoding
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return fn;
+}
+
+// [T, N] row-major array viewed as a 2-D tensor {N (inner), T}; box {32, TT}.
+bool make_strip_map(CUtensorMap* map, CUtensorMapDataType dt, size_t elem, const void* base,
+                    long long T, long long N, int TT) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
+  cuuint64_t strides[1] = {(cuuint64_t)N * elem};
+  cuuint32_t box[2] = {(cuuint32_t)kStripW, (cuuint32_t)TT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename RT, int TT, int S>
+int launch_tma(const void* rewards, const float* values, const uint8_t* resets,
+               const float* last_value, long long T, long long N, double gamma, double gl,
+               float* adv, float* vt, double* stats, void* workspace, cudaStream_t st) {
+  using L = GaeTmaSmem<RT, TT, S>;
+  CUtensorMap tm_r, tm_v, tm_z, tm_a, tm_vt;
+  const CUtensorMapDataType rdt = std::is_same<RT, double>::value
+                                      ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  bool ok = make_strip_map(&tm_r, rdt, sizeof(RT), rewards, T, N, TT) &&
+            make_strip_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, values, T, N, TT) &&
+            make_strip_map(&tm_z, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, resets, T, N, TT) &&
+            make_strip_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, adv, T, N, TT) &&
+            make_strip_map(&tm_vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vt, T, N, TT);
+  if (!ok) {
+    set_error("cuTensorMapEncodeTiled failed for GAE strips (T=%lld N=%lld)", T, N);
+    return DERL_E_CUDA;
+  }
+  auto kern = gae_tma_kernel<RT, TT, S>;
+  static bool attr_set = false;  // once per instantiation; keeps graph captures clean
+  if (!attr_set) {
+    DERL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)L::bytes));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((N + kStripW - 1) / kStripW);
+  kern<<<grid, kStripW, L::bytes, st>>>(tm_r, tm_v, tm_z, tm_a, tm_vt, last_value, (int)T,
+                                        (int)N, gamma, gl, workspace, stats);
+  DERL_LAUNCH_CHECK("gae_tma_kernel");
+  return DERL_OK;
+}
+
+template <typename RT>
+int launch_direct(const void* rewards, const float* values, const uint8_t* resets,
+                  const float* last_value, long long T, long long N, double gamma, double gl,
+                  float* adv, float* vt, double* stats, void* workspace, cudaStream_t st) {
+  constexpr int U = 8;
+  // Few envs: one warp per CTA so that every strip gets an SM to itself.
+  const int block = N <= (long long)sm_count() * 32 * 4 ? 32 : 128;
+  const unsigned grid = (unsigned)((N + block - 1) / block);
+  gae_direct_kernel<RT, U><<<grid, block, 0, st>>>(
+      reinterpret_cast<const RT*>(rewards), values, resets, last_value, T, N, gamma, gl, adv, vt,
+      workspace, stats);
+  DERL_LAUNCH_CHECK("gae_direct_kernel");
+  return DERL_OK;
+}
+
+// ------------------------------------------------------------------ moments / normalise
+__global__ void __launch_bounds__(256)
+moments_kernel(const float* __restrict__ x, long long count, void* workspace, double* stats) {
+  __shared__ double scratch[2 * 32];
+  __shared__ int flag;
+  double s1 = 0.0, s2 = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const double v = (double)__ldg(x + i);
+    s1 += v;
+    s2 += v * v;
+  }
+  finish_stats(s1, s2, (double)count, workspace, stats, scratch, &flag);
+}
+
+// y = (x - mean) / (std + eps): float32 elementwise like NumPy (trajectory_transforms.py:68,
+// :91-92); mean/std come from float64 moments rounded once to float32.
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long count,
+                 const double* __restrict__ stats, double epsilon) {
+  const double n = stats[2];
+  const double mean_d = stats[0] / n;
+  double var_d = stats[1] / n - mean_d * mean_d;
+  var_d = var_d > 0.0 ? var_d : 0.0;
+  const float mean = (float)mean_d;
+  const float denom = (float)((double)(float)sqrt(var_d) + epsilon);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    out[i] = __fdiv_rn(__fsub_rn(x[i], mean), denom);
+  }
+}
+
+unsigned reduce_grid(long long count, int block) {
+  long long want = (count + block - 1) / block;
+  long long cap = (long long)sm_count() * 8;
+  if (want > cap) want = cap;
+  if (want > kMaxReduceBlocks) want = kMaxReduceBlocks;
+  return (unsigned)(want < 1 ? 1 : want);
+}
+
+}  // namespace
+}  // namespace derl
+
+using namespace derl;
+
+extern "C" {
+
+size_t derl_b200_gae_workspace_bytes(int64_t T, int64_t N) {
+  (void)T;
+  if (N < 1) N = 1;
+  const size_t blocks = (size_t)((N + 31) / 32);
+  return kTicketBytes + blocks * 2 * sizeof(double);
+}
+
+size_t derl_b200_moments_workspace_bytes(int64_t count) {
+  (void)count;
+  return kTicketBytes + (size_t)kMaxReduceBlocks * 2 * sizeof(double);
+}
+
+int derl_b200_gae(const void* rewards, int rewards_f64, const float* values,
+                  const uint8_t* resets, const float* last_value, int64_t T, int64_t N,
+                  double gamma, double lambda, float* adv, float* vt, double* stats,
+                  void* workspace, size_t workspace_bytes, int variant, void* stream) {
+  DERL_REQUIRE(T >= 1 && N >= 1, "gae: need T >= 1 and N >= 1 (got T=%lld N=%lld)",
+               (long long)T, (long long)N);
+  DERL_REQUIRE(rewards && values && resets && last_value && adv && vt, "gae: null pointer");
+  DERL_REQUIRE(variant >= DERL_GAE_AUTO && variant <= DERL_GAE_TMA, "gae: bad variant %d",
+               variant);
+  if (stats != nullptr) {
+    DERL_REQUIRE(workspace != nullptr, "gae: stats requested without a workspace");
+    if (workspace_bytes < derl_b200_gae_workspace_bytes(T, N)) {
+      set_error("gae: workspace %zu B < required %zu B", workspace_bytes,
+                derl_b200_gae_workspace_bytes(T, N));
+      return DERL_E_WORKSPACE;
+    }
+  }
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (stats != nullptr) DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+
+  const bool tma_ok = (N % 16 == 0) && N >= 32 && T < (1ll << 31) && N < (1ll << 31) &&
+                      aligned16(rewards) && aligned16(values) && aligned16(resets) &&
+                      aligned16(adv) && aligned16(vt) && encode_tiled_fn() != nullptr;
+  if (variant == DERL_GAE_TMA && !tma_ok) {
+    set_error("gae: TMA variant needs N %% 16 == 0, N >= 32 and 16-byte aligned arrays "
+              "(T=%lld N=%lld)", (long long)T, (long long)N);
+    return DERL_E_INVALID;
+  }
+  const bool use_tma = variant == DERL_GAE_TMA || (variant == DERL_GAE_AUTO && tma_ok);
+  const double gl = gamma * lambda;  // (1*gamma)*lambda, the reference's association (:62)
+  if (use_tma) {
+    return rewards_f64 ? launch_tma<double, 16, 4>(rewards, values, resets, last_value, T, N,
+                                                   gamma, gl, adv, vt, stats, workspace, st)
+                       : launch_tma<float, 16, 4>(rewards, values, resets, last_value, T, N,
+                                                  gamma, gl, adv, vt, stats, workspace, st);
+  }
+  return rewards_f64 ? launch_direct<double>(rewards, values, resets, last_value, T, N, gamma, gl,
+                                             adv, vt, stats, workspace, st)
+                     : launch_direct<float>(rewards, values, resets, last_value, T, N, gamma, gl,
+                                            adv, vt, stats, workspace, st);
+}
+
+int derl_b200_moments(const float* x, int64_t count, double* stats, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  DERL_REQUIRE(count >= 1 && x && stats && workspace, "moments: bad arguments");
+  if (workspace_bytes < derl_b200_moments_workspace_bytes(count)) {
+    set_error("moments: workspace %zu B too small", workspace_bytes);
+    return DERL_E_WORKSPACE;
+  }
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  moments_kernel<<<reduce_grid(count, 256), 256, 0, st>>>(x, count, workspace, stats);
+  DERL_LAUNCH_CHECK("moments_kernel");
+  return DERL_OK;
+}
+
+int derl_b200_normalize(const float* x, float* out, int64_t count, const double* stats,
+                        double epsilon, void* stream) {
+  DERL_REQUIRE(count >= 1 && x && out && stats, "normalize: bad arguments");
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  const long long blocks = (count + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  normalize_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+      x, out, count, stats, epsilon);
+  DERL_LAUNCH_CHECK("normalize_kernel");
+  return DERL_OK;
+}
+
+}  // extern "C"

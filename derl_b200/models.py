@@ -1,0 +1,169 @@
+"""Policy networks of the PPO path, state_dict-compatible with the reference.
+
+Reference: derl/models.py — collocate_inputs :72-91, NatureCNNBase :94-124,
+broadcast_inputs :141-163, NatureCNNModel :166-214, MLP :224-237, MuJoCoModel :240-271,
+make_model :281-298.  Only the options PPO uses are carried (no noisy / dueling /
+distributional heads: those belong to DQN / SAC, outside the hot path).
+
+These layers are the one tensor-core consumer of the update and deliberately stay library
+calls (cuDNN conv / cuBLAS GEMM).  B200-specific choice: an NHWC uint8 frame stack viewed as
+NCHW *is* a channels_last tensor, so the trunk runs channels_last end to end and the
+reference's NCHW `.contiguous()` transpose copy (models.py:123) never happens.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+
+def _device():
+  return "cuda" if torch.cuda.is_available() else "cpu"
+
+
+def orthogonal_init(layer):
+  """Orthogonal weights, zero biases (reference :127-138)."""
+  if hasattr(layer, "weight"):
+    nn.init.orthogonal_(layer.weight)
+  if hasattr(layer, "bias"):
+    nn.init.zeros_(layer.bias)
+
+
+def _collocate(module, inputs, cast_dtype):
+  """NumPy -> tensor, then onto the module's device (and dtype when asked)."""
+  param = next(module.parameters())
+  out = []
+  for x in inputs:
+    if isinstance(x, np.ndarray):
+      x = torch.from_numpy(x)
+    want_dtype = param.dtype if cast_dtype and x.dtype != param.dtype else None
+    if x.device != param.device or want_dtype is not None:
+      x = x.to(device=param.device, dtype=want_dtype)
+    out.append(x)
+  return out
+
+
+def _broadcast(ndims, forward, module, inputs):
+  """Pad leading axes up to `ndims`, call, strip them again (reference :141-163)."""
+  rank = inputs[0].ndim
+  for i, x in enumerate(inputs):
+    if x.ndim != rank:
+      raise ValueError("for broadcasting all inputs must have the same "
+                       "number of dimensions, got "
+                       f"inputs[0].shape={inputs[0].shape}, "
+                       f"inputs[{i}].shape={inputs[i].shape}")
+  extra = ndims - rank
+  outputs = forward(module, *[x[(None,) * extra] for x in inputs])
+
+  def strip(out):
+    if isinstance(out, (tuple, list)):
+      return type(out)(strip(o) for o in out)
+    return out.reshape(out.shape[extra:])
+  return strip(outputs)
+
+
+def _conv_out(size, conv):
+  return (size + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) \
+      // conv.stride[0] + 1
+
+
+class NatureCNNBase(nn.Sequential):
+  """conv8x8/4 -> conv4x4/2 -> conv3x3/1 (ReLU each) -> flatten -> linear 512 (no ReLU)."""
+
+  def __init__(self, input_shape=(84, 84, 4), permute=True):
+    super().__init__()
+    self.permute = permute
+    channels, height, width = input_shape
+    if permute:
+      height, width, channels = input_shape
+    convs = [nn.Conv2d(channels, 32, 8, 4), nn.Conv2d(32, 64, 4, 2), nn.Conv2d(64, 64, 3, 1)]
+    for i, conv in enumerate(convs):
+      height, width = _conv_out(height, conv), _conv_out(width, conv)
+      self.add_module(f"conv-{i}", conv)
+      self.add_module(f"relu-{i}", nn.ReLU())
+    self.add_module("flatten", nn.Flatten())
+    self.add_module("linear", nn.Linear(height * width * convs[-1].out_channels, 512))
+
+  def forward(self, inputs):
+    inputs, = _collocate(self, [inputs], cast_dtype=False)
+    if self.permute:
+      inputs = inputs.permute(0, 3, 1, 2)   # NHWC storage seen as NCHW == channels_last
+    if inputs.dtype == torch.uint8:
+      inputs = inputs.float() / 255         # elementwise: keeps the channels_last strides
+    return super().forward(inputs)
+
+
+class NatureCNNModel(nn.Module):
+  """Nature-DQN trunk with linear heads; `output_units=[A, 1]` for actor-critic PPO."""
+
+  def __init__(self, output_units, input_shape=(84, 84, 4), init_fn=orthogonal_init):
+    super().__init__()
+    self.single_output = not isinstance(output_units, (list, tuple))
+    self.output_units = [output_units] if self.single_output else list(output_units)
+    self.base = NatureCNNBase(input_shape)
+    self.output_layers = nn.ModuleList([nn.Linear(512, n) for n in self.output_units])
+    self.init_fn = init_fn
+    if init_fn:
+      self.apply(init_fn)
+    self.to(_device())
+    if next(self.parameters()).is_cuda:
+      self.to(memory_format=torch.channels_last)
+
+  def _forward(self, observations):
+    hidden = self.base(observations)
+    outputs = [layer(hidden) for layer in self.output_layers]
+    return outputs[0] if self.single_output else outputs
+
+  def forward(self, *inputs):
+    return _broadcast(4, NatureCNNModel._forward, self, inputs)
+
+
+class MLP(nn.Sequential):
+  """Linear/activation stack without an activation after the last layer."""
+
+  def __init__(self, in_features, out_features, hidden_features=(64, 64), activation=nn.Tanh):
+    sizes = (in_features, *hidden_features, out_features)
+    layers = []
+    for nin, nout in zip(sizes[:-1], sizes[1:]):
+      layers += [nn.Linear(nin, nout), activation()]
+    super().__init__(*layers[:-1])
+
+
+class MuJoCoModel(nn.Module):
+  """One MLP per output; state-independent logstd; returns (loc, std[B,D], *others)."""
+
+  def __init__(self, observation_dim, output_units, mlp=MLP, init_fn=orthogonal_init):
+    super().__init__()
+    if not isinstance(output_units, (tuple, list)):
+      output_units = [output_units]
+    self.module_list = nn.ModuleList(mlp(observation_dim, n) for n in output_units)
+    self.init_fn = init_fn
+    if init_fn is not None:
+      self.apply(init_fn)
+    self.logstd = nn.Parameter(torch.zeros(output_units[0]))
+    self.to(_device())
+
+  def _forward(self, observations):
+    observations, = _collocate(self, [observations], cast_dtype=True)
+    first, *others = (module(observations) for module in self.module_list)
+    std = torch.exp(self.logstd)[None].expand(observations.shape[0], -1).contiguous()
+    return (first, std, *others)
+
+  def forward(self, *inputs):
+    return _broadcast(2, MuJoCoModel._forward, self, inputs)
+
+
+def make_model(observation_space, action_space, other_outputs=None, **kwargs):
+  """Default model for the spaces (reference :281-298): Discrete -> NatureCNNModel,
+  Box -> MuJoCoModel.  Spaces are duck-typed (`.n` / `.shape`), gym is not imported."""
+  if isinstance(other_outputs, int) or other_outputs is None:
+    other_outputs = [other_outputs] if other_outputs is not None else []
+  if hasattr(action_space, "spaces"):
+    action_space = action_space.spaces[0]
+  if hasattr(action_space, "n"):
+    return NatureCNNModel(input_shape=observation_space.shape,
+                          output_units=[action_space.n, *other_outputs], **kwargs)
+  if getattr(action_space, "shape", None) is not None:
+    if len(observation_space.shape) != 1 or len(action_space.shape) != 1:
+      raise ValueError(f"expected vector shape, got shape={observation_space.shape}")
+    return MuJoCoModel(observation_dim=observation_space.shape[0],
+                       output_units=[action_space.shape[0], *other_outputs], **kwargs)
+  raise ValueError(f"unsupported action space {action_space}")

@@ -1,0 +1,351 @@
+"""torch.library custom ops (`torch.ops.derl_b200.*`) over the C ABI in include/derl_b200.h.
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream;
+every op body is a pointer hand-off to libderl_b200.so.  The ops are registered for CUDA
+only — called with CPU tensors the dispatcher raises, by design (no CPU fallback).
+"""
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_lib.load()  # fail at import time, loudly, if the CUDA library is absent
+
+_VP = ctypes.c_void_p
+
+
+def _stream(t):
+  return _VP(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+  return _VP(t.data_ptr()) if t is not None and t.numel() > 0 else _VP(None)
+
+
+def _need(cond, msg):
+  if not cond:
+    raise ValueError(msg)
+
+
+def _dense(t, name, dtypes=None):
+  _need(t.is_contiguous(), f"{name} must be contiguous")
+  if dtypes is not None:
+    _need(t.dtype in dtypes, f"{name} must have dtype in {dtypes}, got {t.dtype}")
+  return t
+
+
+class _device_of:
+  """Make the tensor's device current for the duration of a library call."""
+
+  def __init__(self, t):
+    self.idx = t.device.index
+    self.prev = None
+
+  def __enter__(self):
+    cur = torch.cuda.current_device()
+    if self.idx is not None and cur != self.idx:
+      self.prev = cur
+      torch.cuda.set_device(self.idx)
+
+  def __exit__(self, *exc):
+    if self.prev is not None:
+      torch.cuda.set_device(self.prev)
+
+
+# --------------------------------------------------------------------------- K1: GAE
+@torch.library.custom_op("derl_b200::gae", mutates_args=(), device_types="cuda")
+def gae(rewards: Tensor, values: Tensor, resets: Tensor, last_value: Tensor, gamma: float,
+        lambda_: float, want_stats: bool = False,
+        variant: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+  """(advantages [T,N] f32, value_targets [T,N] f32, stats f64[3] or empty)."""
+  _need(values.dim() == 2, f"values must be [T, N], got {tuple(values.shape)}")
+  nsteps, nenvs = values.shape
+  _dense(rewards, "rewards", (torch.float32, torch.float64))
+  _dense(values, "values", (torch.float32,))
+  _dense(resets, "resets", (torch.bool, torch.uint8))
+  _dense(last_value, "last_value", (torch.float32,))
+  _need(rewards.shape == values.shape and resets.shape == values.shape,
+        f"rewards {tuple(rewards.shape)}, resets {tuple(resets.shape)} and values "
+        f"{tuple(values.shape)} must have the same [T, N] shape")
+  _need(last_value.numel() == nenvs, f"last_value must have {nenvs} elements")
+  _need(nsteps >= 1 and nenvs >= 1, "empty rollout")
+  lib = _lib.load()
+  adv = torch.empty_like(values)
+  targets = torch.empty_like(values)
+  if want_stats:
+    stats = torch.empty(_lib.GAE_STATS, dtype=torch.float64, device=values.device)
+    ws_bytes = lib.derl_b200_gae_workspace_bytes(nsteps, nenvs)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=values.device)
+  else:
+    stats = torch.empty(0, dtype=torch.float64, device=values.device)
+    ws_bytes, ws = 0, None
+  with _device_of(values):
+    _lib.check(lib.derl_b200_gae(_p(rewards), int(rewards.dtype == torch.float64), _p(values),
+                                 _p(resets), _p(last_value), nsteps, nenvs, float(gamma),
+                                 float(lambda_), _p(adv), _p(targets), _p(stats), _p(ws),
+                                 ws_bytes, int(variant), _stream(values)), "gae")
+  return adv, targets, stats
+
+
+@gae.register_fake
+def _(rewards, values, resets, last_value, gamma, lambda_, want_stats=False, variant=0):
+  stats = values.new_empty(_lib.GAE_STATS if want_stats else 0, dtype=torch.float64)
+  return torch.empty_like(values), torch.empty_like(values), stats
+
+
+@torch.library.custom_op("derl_b200::moments", mutates_args=(), device_types="cuda")
+def moments(x: Tensor) -> Tensor:
+  """float64 {sum, sum of squares, count} of a float32 tensor."""
+  _dense(x, "x", (torch.float32,))
+  _need(x.numel() >= 1, "moments of an empty tensor")
+  lib = _lib.load()
+  stats = torch.empty(3, dtype=torch.float64, device=x.device)
+  ws_bytes = lib.derl_b200_moments_workspace_bytes(x.numel())
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+  with _device_of(x):
+    _lib.check(lib.derl_b200_moments(_p(x), x.numel(), _p(stats), _p(ws), ws_bytes, _stream(x)),
+               "moments")
+  return stats
+
+
+@moments.register_fake
+def _(x):
+  return x.new_empty(3, dtype=torch.float64)
+
+
+@torch.library.custom_op("derl_b200::normalize", mutates_args=(), device_types="cuda")
+def normalize(x: Tensor, stats: Tensor, epsilon: float) -> Tensor:
+  """(x - mean) / (std_pop + epsilon) from device-resident {sum, sumsq, count}."""
+  _dense(x, "x", (torch.float32,))
+  _dense(stats, "stats", (torch.float64,))
+  _need(stats.numel() >= 3 and x.numel() >= 1, "normalize: bad stats or empty input")
+  out = torch.empty_like(x)
+  with _device_of(x):
+    _lib.check(_lib.load().derl_b200_normalize(_p(x), _p(out), x.numel(), _p(stats),
+                                               float(epsilon), _stream(x)), "normalize")
+  return out
+
+
+@normalize.register_fake
+def _(x, stats, epsilon):
+  return torch.empty_like(x)
+
+
+# --------------------------------------------------------------------------- K2: gather
+@torch.library.custom_op("derl_b200::gather_rows", mutates_args=(), device_types="cuda")
+def gather_rows(src: Tensor, perm: Tensor, start: int, count: int) -> Tensor:
+  """out[j] = src[perm[start + j]] along dim 0 (bit-exact copy of whole rows)."""
+  _dense(src, "src")
+  _dense(perm, "perm", (torch.int64,))
+  _need(src.dim() >= 1 and src.shape[0] >= 1, "src must have at least one row")
+  _need(0 <= start and 0 <= count and start + count <= perm.numel(),
+        f"window [{start}, {start + count}) outside perm of {perm.numel()}")
+  out = src.new_empty((count,) + tuple(src.shape[1:]))
+  row_bytes = src[0].numel() * src.element_size()
+  if count == 0 or row_bytes == 0:
+    return out
+  with _device_of(src):
+    _lib.check(_lib.load().derl_b200_gather_rows(_p(src), src.shape[0], row_bytes, _p(perm),
+                                                 start, count, _p(out), _stream(src)),
+               "gather_rows")
+  return out
+
+
+@gather_rows.register_fake
+def _(src, perm, start, count):
+  return src.new_empty((count,) + tuple(src.shape[1:]))
+
+
+@torch.library.custom_op("derl_b200::gather_columns", mutates_args=(), device_types="cuda")
+def gather_columns(columns: List[Tensor], perm: Tensor, start: int, count: int,
+                   moments_col: int = -1) -> List[Tensor]:
+  """Gathers every narrow column in one launch; the returned list has one extra trailing
+  entry: float64 {sum, sumsq, count} of columns[moments_col] over the gathered rows (empty
+  when moments_col < 0)."""
+  ncol = len(columns)
+  _need(1 <= ncol <= _lib.MAX_COLUMNS, f"between 1 and {_lib.MAX_COLUMNS} columns, got {ncol}")
+  _dense(perm, "perm", (torch.int64,))
+  _need(0 <= start and 0 <= count and start + count <= perm.numel(),
+        f"window [{start}, {start + count}) outside perm of {perm.numel()}")
+  dev = columns[0].device
+  outs, row_bytes = [], []
+  for i, col in enumerate(columns):
+    _dense(col, f"columns[{i}]")
+    _need(col.dim() >= 1 and col.shape[0] >= 1, f"columns[{i}] has no rows")
+    outs.append(col.new_empty((count,) + tuple(col.shape[1:])))
+    row_bytes.append(col[0].numel() * col.element_size())
+    _need(row_bytes[-1] >= 1, f"columns[{i}] has empty rows")
+  lib = _lib.load()
+  if moments_col >= 0:
+    _need(columns[moments_col].dtype == torch.float32 and row_bytes[moments_col] == 4,
+          "moments column must be float32 with one element per row")
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    ws_bytes = lib.derl_b200_moments_workspace_bytes(count)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  else:
+    stats, ws_bytes, ws = torch.empty(0, dtype=torch.float64, device=dev), 0, None
+  if count > 0:
+    srcs = (_VP * ncol)(*[c.data_ptr() for c in columns])
+    dsts = (_VP * ncol)(*[o.data_ptr() for o in outs])
+    rbs = (ctypes.c_int64 * ncol)(*row_bytes)
+    with _device_of(columns[0]):
+      _lib.check(lib.derl_b200_gather_columns(ncol, srcs, rbs, dsts, _p(perm), start, count,
+                                              int(moments_col), _p(stats), _p(ws), ws_bytes,
+                                              _stream(columns[0])), "gather_columns")
+  return outs + [stats]
+
+
+@gather_columns.register_fake
+def _(columns, perm, start, count, moments_col=-1):
+  outs = [c.new_empty((count,) + tuple(c.shape[1:])) for c in columns]
+  return outs + [columns[0].new_empty(3 if moments_col >= 0 else 0, dtype=torch.float64)]
+
+
+# --------------------------------------------------------------------------- K3: PPO loss
+def _loss_common(head, values, old_log_prob, advantages, value_targets, old_values):
+  ref = head if head is not None else values
+  _need(ref is not None, "ppo_loss: both the policy head and the value head are absent")
+  nb = ref.shape[0]
+  if head is not None:
+    _need(old_log_prob is not None and advantages is not None,
+          "ppo_loss: policy head needs log_prob and advantages")
+    _dense(old_log_prob, "log_prob", (torch.float32,))
+    _dense(advantages, "advantages", (torch.float32,))
+    _need(old_log_prob.numel() == nb and advantages.numel() == nb,
+          "ppo_loss: log_prob / advantages length differs from the batch size")
+  if values is not None:
+    _need(value_targets is not None and old_values is not None,
+          "ppo_loss: value head needs value_targets and old values")
+    for name, t in (("values", values), ("value_targets", value_targets),
+                    ("old values", old_values)):
+      _dense(t, name, (torch.float32,))
+      _need(t.numel() == nb, f"ppo_loss: {name} must have one element per sample")
+  return nb
+
+
+def _loss_buffers(ref, nb):
+  lib = _lib.load()
+  loss = torch.empty((), dtype=torch.float32, device=ref.device)
+  stats = torch.empty(_lib.LOSS_STATS, dtype=torch.float32, device=ref.device)
+  ws_bytes = lib.derl_b200_ppo_loss_workspace_bytes(nb)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device)
+  return lib, loss, stats, ws, ws_bytes
+
+
+@torch.library.custom_op("derl_b200::ppo_loss_categorical", mutates_args=(), device_types="cuda")
+def ppo_loss_categorical(logits: Optional[Tensor], values: Optional[Tensor],
+                         actions: Optional[Tensor], old_log_prob: Optional[Tensor],
+                         advantages: Optional[Tensor], value_targets: Optional[Tensor],
+                         old_values: Optional[Tensor], cliprange: Optional[float],
+                         value_loss_coef: float,
+                         entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+  """(loss [], dloss/dlogits, dloss/dvalues, stats f32[16]); absent heads give empty grads."""
+  nb = _loss_common(logits, values, old_log_prob, advantages, value_targets, old_values)
+  ref = logits if logits is not None else values
+  nact = 1
+  if logits is not None:
+    _dense(logits, "logits", (torch.float32,))
+    _need(logits.dim() == 2, f"logits must be [B, A], got {tuple(logits.shape)}")
+    nact = logits.shape[1]
+    _need(actions is not None, "ppo_loss_categorical: actions missing")
+    _dense(actions, "actions", (torch.int64,))
+    _need(actions.numel() == nb, "ppo_loss_categorical: one action index per sample")
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  dlogits = torch.empty_like(logits) if logits is not None else ref.new_empty(0)
+  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
+  with _device_of(ref):
+    _lib.check(lib.derl_b200_ppo_loss_categorical(
+        _p(logits), nb, nact, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
+        _p(value_targets), _p(old_values), int(cliprange is not None),
+        float(cliprange or 0.), float(value_loss_coef), float(entropy_coef), _p(loss),
+        _p(dlogits), _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref)),
+        "ppo_loss_categorical")
+  return loss, dlogits, dvalues, stats
+
+
+@ppo_loss_categorical.register_fake
+def _(logits, values, actions, old_log_prob, advantages, value_targets, old_values, cliprange,
+      value_loss_coef, entropy_coef):
+  ref = logits if logits is not None else values
+  return (ref.new_empty(()), torch.empty_like(logits) if logits is not None else ref.new_empty(0),
+          torch.empty_like(values) if values is not None else ref.new_empty(0),
+          ref.new_empty(_lib.LOSS_STATS))
+
+
+def _cat_setup(ctx, inputs, output):
+  ctx.set_materialize_grads(False)
+  ctx.save_for_backward(output[1], output[2])
+  ctx.has = (inputs[0] is not None, inputs[1] is not None)
+
+
+def _cat_backward(ctx, g_loss, g_dlogits, g_dvalues, g_stats):
+  dlogits, dvalues = ctx.saved_tensors
+  none8 = (None,) * 8
+  if g_loss is None:
+    return (None, None) + none8
+  return ((g_loss * dlogits) if ctx.has[0] else None,
+          (g_loss * dvalues) if ctx.has[1] else None) + none8
+
+
+ppo_loss_categorical.register_autograd(_cat_backward, setup_context=_cat_setup)
+
+
+@torch.library.custom_op("derl_b200::ppo_loss_gaussian", mutates_args=(), device_types="cuda")
+def ppo_loss_gaussian(loc: Optional[Tensor], scale: Optional[Tensor], values: Optional[Tensor],
+                      actions: Optional[Tensor], old_log_prob: Optional[Tensor],
+                      advantages: Optional[Tensor], value_targets: Optional[Tensor],
+                      old_values: Optional[Tensor], cliprange: Optional[float],
+                      value_loss_coef: float,
+                      entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+  """(loss [], dloss/dloc, dloss/dscale, dloss/dvalues, stats f32[16])."""
+  nb = _loss_common(loc, values, old_log_prob, advantages, value_targets, old_values)
+  ref = loc if loc is not None else values
+  ndim = 1
+  if loc is not None:
+    _need(scale is not None and actions is not None, "ppo_loss_gaussian: scale/actions missing")
+    for name, t in (("loc", loc), ("scale", scale), ("actions", actions)):
+      _dense(t, name, (torch.float32,))
+    _need(loc.dim() == 2 and scale.shape == loc.shape and actions.shape == loc.shape,
+          f"loc {tuple(loc.shape)}, scale {tuple(scale.shape)} and actions "
+          f"{tuple(actions.shape)} must all be [B, D]")
+    ndim = loc.shape[1]
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  dloc = torch.empty_like(loc) if loc is not None else ref.new_empty(0)
+  dscale = torch.empty_like(scale) if loc is not None else ref.new_empty(0)
+  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
+  with _device_of(ref):
+    _lib.check(lib.derl_b200_ppo_loss_gaussian(
+        _p(loc), _p(scale), nb, ndim, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
+        _p(value_targets), _p(old_values), int(cliprange is not None), float(cliprange or 0.),
+        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc), _p(dscale),
+        _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref)), "ppo_loss_gaussian")
+  return loss, dloc, dscale, dvalues, stats
+
+
+@ppo_loss_gaussian.register_fake
+def _(loc, scale, values, actions, old_log_prob, advantages, value_targets, old_values,
+      cliprange, value_loss_coef, entropy_coef):
+  ref = loc if loc is not None else values
+  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
+  return ref.new_empty(()), grad(loc), grad(scale), grad(values), ref.new_empty(_lib.LOSS_STATS)
+
+
+def _gauss_setup(ctx, inputs, output):
+  ctx.set_materialize_grads(False)
+  ctx.save_for_backward(output[1], output[2], output[3])
+  ctx.has = (inputs[0] is not None, inputs[2] is not None)
+
+
+def _gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
+  dloc, dscale, dvalues = ctx.saved_tensors
+  none8 = (None,) * 8
+  if g_loss is None:
+    return (None, None, None) + none8
+  return ((g_loss * dloc) if ctx.has[0] else None, (g_loss * dscale) if ctx.has[0] else None,
+          (g_loss * dvalues) if ctx.has[1] else None) + none8
+
+
+ppo_loss_gaussian.register_autograd(_gauss_backward, setup_context=_gauss_setup)

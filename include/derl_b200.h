@@ -1,0 +1,191 @@
+/*
+ * derl_b200 — C ABI of the B200 (sm_100a) PPO rollout-processing / update data path.
+ *
+ * The reference (mknbv/derl) is pure Python and has no FFI of its own; its boundary for
+ * this path is three duck-typed Python protocols.  This header is the
+ * native boundary *underneath* those protocols: each entry point replaces the arithmetic
+ * of one reference function and is what a binding in the reference's own tree would call
+ * (ctypes stub in INTEGRATION.md).  Citations are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every `*_dev` pointer is DEVICE memory of the
+ *     current CUDA device, every `*_host` pointer is HOST memory;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *     device entry points only enqueue work, they never synchronise;
+ *   - inputs are borrowed and never written; outputs must not alias inputs;
+ *   - return value: 0 on success, a DERL_E_* code otherwise; `derl_b200_last_error()`
+ *     then returns a thread-local human-readable message;
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails with
+ *     DERL_E_NO_DEVICE.
+ */
+#ifndef DERL_B200_H_
+#define DERL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DERL_B200_ABI_VERSION 1
+
+enum {
+  DERL_OK = 0,
+  DERL_E_INVALID = 1,   /* bad argument (null pointer, negative size, unsupported width) */
+  DERL_E_NO_DEVICE = 2, /* no CUDA device, or device is not compute capability 10.x     */
+  DERL_E_CUDA = 3,      /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  DERL_E_WORKSPACE = 4  /* caller-provided workspace too small                           */
+};
+
+/* GAE kernel variants (derl_b200_gae `variant`). AUTO picks TMA when shapes allow it. */
+enum {
+  DERL_GAE_AUTO = 0,
+  DERL_GAE_DIRECT = 1, /* one lane per env, register-prefetched coalesced loads          */
+  DERL_GAE_TMA = 2     /* one lane per env, [T_tile x 32 env] tiles staged through smem   */
+                       /* by TMA (cp.async.bulk.tensor) with an mbarrier pipeline         */
+};
+
+/* ------------------------------------------------------------------ library / device */
+
+int derl_b200_abi_version(void);
+const char* derl_b200_last_error(void);
+/* 0 when the current device is an sm_100 part this library has code for. */
+int derl_b200_device_ok(void);
+/* Number of kernels this library has launched in this process (bench.py `gpu_launches`). */
+uint64_t derl_b200_launch_count(void);
+
+/* ------------------------------------------------------------------ K1: GAE / returns
+ * Replaces the arithmetic of GAE.__call__, derl/runners/trajectory_transforms.py:45-65
+ * (reverse scan :56-62, two-step last row :46,:53, value_targets :63), bit-exactly:
+ * float64 register arithmetic in NumPy's evaluation order, no FMA contraction, float32
+ * stores.  Layout is time-major [T, N] (flat index t*N + n), N = number of envs.
+ *
+ *   rewards_dev     [T,N] float32 (rewards_f64 = 0) or float64 (rewards_f64 = 1)
+ *   values_dev      [T,N] float32     (trailing size-1 axis already squeezed, :42-43)
+ *   resets_dev      [T,N] uint8/bool  (nonzero = episode ended at this step)
+ *   last_value_dev  [N]   float32     (policy.act(latest_observations)["values"], :47-52)
+ *   advantages_dev  [T,N] float32 out (pre-normalisation GAE)
+ *   value_targets_dev [T,N] float32 out (= advantages + values in float32, :63)
+ *   stats_dev       NULL, or [DERL_GAE_STATS] float64 out: {sum(adv), sum(adv^2), count}
+ *                   accumulated in float64, deterministic order (no float atomics);
+ *                   feeds derl_b200_normalize for the `normalize` branch (:67-68)
+ *   workspace_dev   NULL iff stats_dev is NULL; else >= derl_b200_gae_workspace_bytes(T,N)
+ */
+#define DERL_GAE_STATS 3
+size_t derl_b200_gae_workspace_bytes(int64_t T, int64_t N);
+int derl_b200_gae(const void* rewards_dev, int rewards_f64, const float* values_dev,
+                  const uint8_t* resets_dev, const float* last_value_dev, int64_t T,
+                  int64_t N, double gamma, double lambda, float* advantages_dev,
+                  float* value_targets_dev, double* stats_dev, void* workspace_dev,
+                  size_t workspace_bytes, int variant, void* stream);
+
+/* Whole-array normalisation x <- (x - mean) / (std_pop + eps) in float32 from float64
+ * {sum, sumsq, count} held in DEVICE memory (no host sync).  Replaces
+ * trajectory_transforms.py:67-68 (whole rollout) and NormalizeAdvantages.__call__
+ * :89-92 (per minibatch).  In-place allowed (out_dev == x_dev). */
+int derl_b200_normalize(const float* x_dev, float* out_dev, int64_t count,
+                        const double* stats_dev, double epsilon, void* stream);
+
+/* {sum, sumsq, count} of a float32 vector, float64 accumulation, deterministic.
+ * workspace_dev >= derl_b200_moments_workspace_bytes(count). */
+size_t derl_b200_moments_workspace_bytes(int64_t count);
+int derl_b200_moments(const float* x_dev, int64_t count, double* stats_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K2: minibatch gather
+ * Replaces the two NumPy fancy-index copies of IterateWithMinibatches
+ * (derl/runners/onpolicy.py:44-49 epoch shuffle, :57-62 minibatch slice) with ONE
+ * permutation-indexed copy out of the resident, never-shuffled rollout:
+ *     dst[j, :] = src[perm[start + j], :]      for j in [0, count)
+ * `perm` is the epoch's composed permutation (int64, device).  Bit-exact by construction.
+ *
+ * derl_b200_gather_rows: one wide column (frame stacks: row_bytes = 84*84*4 = 28224).
+ *   When row_bytes % 16 == 0 and src/dst are 16-byte aligned the rows move through shared
+ *   memory with TMA bulk copies (cp.async.bulk, mbarrier-pipelined, persistent CTAs);
+ *   otherwise a vectorised LDG/STG kernel is used.  n_src_rows bounds the indices (debug
+ *   builds trap on out-of-range; release trusts the caller like NumPy would raise).
+ */
+int derl_b200_gather_rows(const void* src_dev, int64_t n_src_rows, int64_t row_bytes,
+                          const int64_t* perm_dev, int64_t start, int64_t count,
+                          void* dst_dev, void* stream);
+
+/* derl_b200_gather_columns: up to DERL_MAX_COLUMNS narrow columns (actions, log_prob,
+ * advantages, value_targets, values, rewards, resets ...) in one launch.  Column c has
+ * row_bytes[c] bytes per sample.  If moments_col >= 0 that column must be float32 with
+ * row_bytes 4 and its {sum, sumsq, count} over the gathered minibatch is written to
+ * stats_dev (float64[3]) — the fused statistics pass of NormalizeAdvantages
+ * (trajectory_transforms.py:89-92).  workspace_dev >= derl_b200_moments_workspace_bytes(count).
+ */
+#define DERL_MAX_COLUMNS 16
+int derl_b200_gather_columns(int n_columns, const void* const* src_dev,
+                             const int64_t* row_bytes, void* const* dst_dev,
+                             const int64_t* perm_dev, int64_t start, int64_t count,
+                             int moments_col, double* stats_dev, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K3: fused PPO loss
+ * Replaces PPOLoss.__call__ (derl/alg/ppo.py:100-108) = policy_loss (:31-64) +
+ * value_loss_coef * value_loss (:73-98) together with the torch.distributions calls it
+ * makes (Categorical / Independent(Normal) log_prob + entropy, derl/policies.py:42,64-66)
+ * and with its autograd backward: one launch yields the scalar loss AND d loss/d inputs.
+ *
+ *   loss = mean_i max(-r_i*adv_i, -clamp(r_i, 1-clip, 1+clip)*adv_i) - ecoef * mean_i H_i
+ *        + vcoef * mean_i max((v_i-vt_i)^2, (vold_i + clamp(v_i-vold_i, -clip, clip) - vt_i)^2)
+ *   r_i = exp(logp_i(action_i) - old_logp_i);  has_clip = 0 drops both clipped branches
+ *   (cliprange=None, ppo.py:47,83).  torch.max tie semantics (gradient split 1/2 : 1/2) kept.
+ *
+ * All vectors are float32 device arrays of length B unless noted; values/value_targets/
+ * old_values may be the reference's [B,1] arrays (same memory).  Gradients already include
+ * the 1/B of the means.  Reductions are float64, two-stage, deterministic.
+ *
+ *   stats_dev [DERL_LOSS_STATS] float32 out — the scalars the reference logs
+ *   (ppo.py:57-59, 91-94, 106):
+ *     [0] loss  [1] mean max(s1,s2) ("policy_loss")  [2] mean entropy  [3] value_loss
+ *     [4] mean(advantages)  [5] mean(value_targets)  [6] mean(values)
+ *     [7] r_squared = 1 - mean((v-vt)^2)/var_unbiased(v)   (derl/alg/common.py:9-12)
+ *     [8] fraction of samples with ratio outside [1-clip, 1+clip]
+ *     [9] mean(old_logp - logp)  (approximate KL)
+ *   loss_dev [1] float32 out.   Either head may be skipped: pass logits_dev (or loc_dev) NULL
+ *   for a value-only loss (PPOLoss.value_loss) or values_dev NULL for a policy-only loss
+ *   (PPOLoss.policy_loss); the corresponding gradient pointers must then be NULL as well.
+ *   workspace_dev >= derl_b200_ppo_loss_workspace_bytes(B).
+ */
+#define DERL_LOSS_STATS 16
+size_t derl_b200_ppo_loss_workspace_bytes(int64_t B);
+
+/* Categorical head: logits [B,A] float32 row-major, actions [B] int64, 1 <= A <= 1024. */
+int derl_b200_ppo_loss_categorical(const float* logits_dev, int64_t B, int64_t A,
+                                   const int64_t* actions_dev, const float* old_logp_dev,
+                                   const float* advantages_dev, const float* values_dev,
+                                   const float* value_targets_dev, const float* old_values_dev,
+                                   int has_clip, double cliprange, double value_loss_coef,
+                                   double entropy_coef, float* loss_dev, float* dlogits_dev,
+                                   float* dvalues_dev, float* stats_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream);
+
+/* Diagonal-Gaussian head: loc, scale, actions [B,D] float32 row-major, 1 <= D <= 256. */
+int derl_b200_ppo_loss_gaussian(const float* loc_dev, const float* scale_dev, int64_t B,
+                                int64_t D, const float* actions_dev, const float* old_logp_dev,
+                                const float* advantages_dev, const float* values_dev,
+                                const float* value_targets_dev, const float* old_values_dev,
+                                int has_clip, double cliprange, double value_loss_coef,
+                                double entropy_coef, float* loss_dev, float* dloc_dev,
+                                float* dscale_dev, float* dvalues_dev, float* stats_dev,
+                                void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer entry points
+ * Same operations on HOST arrays (what a NumPy caller such as the reference's
+ * TransformInteractions hook holds): the library allocates device scratch, copies in on
+ * `stream`, runs the kernel, copies out and synchronises the stream before returning.
+ * `normalize` != 0 additionally applies the whole-rollout normalisation (:67-68).
+ */
+int derl_b200_gae_host(const void* rewards_host, int rewards_f64, const float* values_host,
+                       const uint8_t* resets_host, const float* last_value_host, int64_t T,
+                       int64_t N, double gamma, double lambda, int normalize, double epsilon,
+                       float* advantages_host, float* value_targets_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DERL_B200_H_ */
