@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — PPO update throughput of the B200-native data path (and its CPU reference arm).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (port)
+
+A *step* is one pass of the hot path over one synthetic rollout (BASELINE.json configs[2],
+weak-scaled: 4096 envs x 128 steps of 84x84x4 uint8 frame stacks PER GPU; at 8 GPUs this is
+configs[3]'s 32768 envs):  bootstrap value -> GAE kernel -> 4 epochs x 4 minibatches of
+[permutation gather -> advantage normalisation -> NatureCNN forward -> fused PPO loss
+fwd+bwd -> network backward -> (NCCL gradient all-reduce) -> clip_grad_norm -> Adam].
+Nothing is skipped and the numbers come from the public API (ppo_runner_wrap + PPO.step).
+
+value  = samples consumed by the update (T*N*epochs, all ranks) / device time, rollout
+         already resident in HBM when the timed region starts.
+e2e    = same, rollout starting in pinned HOST memory (NumPy arrays, as the reference's
+         EnvRunner hands them over): the H2D upload of the whole rollout and the D2H of
+         bootstrap values + losses are inside the timed region.
+roofline = the dominant hand-written kernel (TMA row gather), algorithmic bytes / CUDA-event
+         time inside the timed region, against MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+OBS_ROW_BYTES = 84 * 84 * 4
+# PPO atari defaults of the reference (derl/factory/ppo.py:20-34); epochs x minibatches per
+# BASELINE.json configs[0] ("4 epochs x 4 minibatches")
+HP = dict(gamma=0.99, lambda_=0.95, cliprange=0.1, value_loss_coef=0.25, entropy_coef=0.01,
+          max_grad_norm=0.5, lr=2.5e-4, eps=1e-5)
+
+
+def parse_args():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=3)
+  p.add_argument("--warmup", type=int, default=3)
+  p.add_argument("--impl", choices=("ours", "reference"), default="ours")
+  p.add_argument("--envs-per-gpu", type=int, default=4096)
+  p.add_argument("--horizon", type=int, default=128)
+  p.add_argument("--epochs", type=int, default=4)
+  p.add_argument("--minibatches", type=int, default=4)
+  p.add_argument("--nactions", type=int, default=4)
+  p.add_argument("--micro-batch", type=int, default=16384)
+  p.add_argument("--net", choices=("tf32", "fp32", "bf16"), default="tf32",
+                 help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
+  p.add_argument("--cpu-envs", type=int, default=32,
+                 help="envs of the bounded CPU-baseline sample (same horizon/epochs/minibatches)")
+  p.add_argument("--no-e2e", action="store_true")
+  p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--gae-sweep", action="store_true", help="also time the GAE kernel sweep")
+  return p.parse_args()
+
+
+def peaks():
+  path = os.path.join(REPO, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+  """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+  FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+            "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index, self.proc, self.lines = index, None, []
+
+  def __enter__(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+           "--format=csv,noheader,nounits", "-lms", "200"],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+    return self
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def __exit__(self, *exc):
+    if self.proc is not None:
+      time.sleep(0.25)
+      self.proc.terminate()
+      self.thread.join(timeout=2)
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    for line in self.lines:
+      parts = [x.strip() for x in line.split(",")]
+      if len(parts) != 6:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for name, flag in zip(names, parts[2:]):
+        if flag.lower().startswith("active"):
+          reasons.add(name)
+    if not sm:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_update_throughput(args, nenvs, steps, warmup):
+  """The reference's CPU path (oracle port: NumPy GAE/shuffle/slice/normalise + CPU torch
+  NatureCNN/PPOLoss/Adam) on a bounded sample of the workload; returns samples/s."""
+  from oracle import derl_oracle as O
+  import derl_b200 as d
+  torch.manual_seed(0)
+  model = O.NatureCNN(args.nactions)
+  optimizer = torch.optim.Adam(model.parameters(), lr=HP["lr"], eps=HP["eps"])
+  rollout = d.make_rollout("atari", args.horizon, nenvs, device="cpu", seed=0,
+                           nactions=args.nactions)
+  latest = torch.from_numpy(rollout["state"]["latest_observations"])
+  columns = {k: v for k, v in rollout.items() if k != "state"}
+  np.random.seed(0)
+  times = []
+  for it in range(warmup + steps):
+    t0 = time.perf_counter()
+    with torch.no_grad():
+      last_value = model(latest)[-1].numpy()
+    O.ppo_update(model, optimizer, columns, last_value, gamma=HP["gamma"],
+                 lambda_=HP["lambda_"], num_epochs=args.epochs,
+                 num_minibatches=args.minibatches, cliprange=HP["cliprange"],
+                 value_loss_coef=HP["value_loss_coef"], entropy_coef=HP["entropy_coef"],
+                 max_grad_norm=HP["max_grad_norm"])
+    if it >= warmup:
+      times.append(time.perf_counter() - t0)
+  samples = args.horizon * nenvs * args.epochs
+  return samples * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args, rank):
+  if rank != 0:
+    return
+  value, sec = cpu_update_throughput(args, args.cpu_envs, args.steps, min(args.warmup, 1))
+  cores = torch.get_num_threads()
+  sample = (f"{args.cpu_envs} envs x {args.horizon} steps (of {args.envs_per_gpu} per GPU), "
+            f"{args.epochs} epochs x {args.minibatches} minibatches, NatureCNN fp32, full update")
+  line = {
+      "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value,
+      "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+      "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f32 (GAE f64 registers)", "data": "synthetic",
+      "config": workload_config(args, args.gpus),
+      "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+  return {"workload": (f"atari-shaped PPO update, {args.envs_per_gpu} envs/GPU x {args.horizon} "
+                       f"steps, 84x84x4 u8 obs, {args.epochs} epochs x {args.minibatches} "
+                       f"minibatches, NatureCNN A={args.nactions} (BASELINE configs[2]; "
+                       f"{args.envs_per_gpu * world} envs total)"),
+          "envs_total": args.envs_per_gpu * world, "horizon": args.horizon,
+          "epochs": args.epochs, "minibatches": args.minibatches,
+          "micro_batch": args.micro_batch, "network": args.net,
+          "l2": "inputs >> L2 (14.8 GB rollout per GPU; every minibatch reads fresh rows)",
+          "parallelism": f"env-axis dp{world}"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def build_alg(args, d, source, world, device):
+  model = source.policy.model
+  sync = None
+  group_norm = None
+  if world > 1:
+    from derl_b200 import parallel
+    sync = parallel.GradientAllReduce(model)
+    group_norm = torch.distributed.group.WORLD
+  transforms = [d.GAE(source.policy, gamma=HP["gamma"], lambda_=HP["lambda_"], normalize=False),
+                d.MergeTimeBatch()]
+  runner = d.TransformInteractions(source, transforms)
+  runner = d.IterateWithMinibatches(runner, args.epochs, args.minibatches)
+  runner = d.TransformInteractions(runner, [d.NormalizeAdvantages(group=group_norm)])
+  optimizer = torch.optim.Adam(model.parameters(), lr=HP["lr"], eps=HP["eps"], fused=True)
+  anneal = d.LinearAnneal(HP["lr"], 10e6 * 100, name="lr")
+
+  class GroupLR:  # LinearAnneal -> optimizer.param_groups (host float; closed-form step_to)
+    name = "lr"
+
+    def step_to(self, n):
+      anneal.step_to(n)
+      for group in optimizer.param_groups:
+        group["lr"] = float(anneal.get_tensor())
+
+    def summarize(self, n):
+      pass
+
+  trainer = d.Trainer(optimizer, anneals=[GroupLR()], max_grad_norm=HP["max_grad_norm"],
+                      grad_sync=sync, micro_batch=args.micro_batch)
+  alg = d.PPO(runner, trainer, cliprange=HP["cliprange"],
+              value_loss_coef=HP["value_loss_coef"], entropy_coef=HP["entropy_coef"])
+  return alg, runner
+
+
+class HostRolloutSource:
+  """EnvRunner-like source whose arrays live in pinned host memory (NumPy views)."""
+
+  def __init__(self, policy, device_rollout, nenvs, horizon):
+    self.policy, self.horizon, self.nenvs = policy, horizon, nenvs
+    self.env = type("E", (), {"nenvs": nenvs, "unwrapped": property(lambda s: s)})()
+    self.nsteps, self.step_count = None, 0
+    self.host = {}
+    self.bytes = 0
+    for key, val in device_rollout.items():
+      if key == "state":
+        continue
+      pinned = torch.empty(val.shape, dtype=val.dtype, pin_memory=True)
+      pinned.copy_(val)
+      self.host[key] = pinned.numpy()
+      self.bytes += pinned.numel() * pinned.element_size()
+    latest = device_rollout["state"]["latest_observations"]
+    pinned = torch.empty(latest.shape, dtype=latest.dtype, pin_memory=True)
+    pinned.copy_(latest)
+    self.latest = pinned.numpy()
+    self.bytes += pinned.numel() * pinned.element_size()
+
+  def is_exhausted(self):
+    return False
+
+  def run(self, obs=None):
+    while True:
+      self.step_count += self.horizon * self.nenvs
+      out = dict(self.host)
+      out["state"] = dict(latest_observations=self.latest)
+      yield out
+
+
+def one_update(alg, runner_iter, nbatches):
+  losses = []
+  for _ in range(nbatches):
+    losses.append(alg.step(next(runner_iter)))
+  return losses
+
+
+def timed_updates(alg, runner, nbatches, steps, warmup, world, read_losses):
+  """W untimed + K timed steps, barrier + synchronize on both sides, CUDA events, max over
+  ranks.  Returns (seconds for K steps, losses of the last step)."""
+  it = runner.run()
+  losses = None
+  for _ in range(warmup):
+    losses = one_update(alg, it, nbatches)
+  if world > 1:
+    torch.distributed.barrier()
+  torch.cuda.synchronize()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  start.record()
+  for _ in range(steps):
+    losses = one_update(alg, it, nbatches)
+    if read_losses:  # D2H read of the step's result inside the timed region
+      losses = torch.stack([l.detach() for l in losses]).cpu()
+  stop.record()
+  torch.cuda.synchronize()
+  if world > 1:
+    torch.distributed.barrier()
+  sec = start.elapsed_time(stop) / 1e3
+  if world > 1:
+    t = torch.tensor([sec], device="cuda")
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = float(t)
+  return sec, losses
+
+
+def kernel_times(profile):
+  """name -> (launches, mean ms) from the (name, start, end) event triples."""
+  out = {}
+  for name, start, end in profile:
+    out.setdefault(name, []).append(start.elapsed_time(end))
+  return {k: (len(v), float(np.mean(v))) for k, v in out.items()}
+
+
+def gae_sweep(d, hbm_peak):
+  """BASELINE configs[4]: GAE kernel alone, T x N sweep, 17 B/element, L2 flushed between
+  launches by a 256 MB memset (inputs of the large sizes exceed L2 anyway)."""
+  K = torch.ops.derl_b200
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+  rows = []
+  for nsteps in (128, 512, 2048):
+    for nenvs in (8, 512, 4096, 32768, 65536):
+      if nsteps * nenvs > (1 << 27):
+        continue
+      gen = torch.Generator(device="cuda").manual_seed(1)
+      rewards = torch.randn(nsteps, nenvs, device="cuda", generator=gen)
+      values = torch.randn(nsteps, nenvs, device="cuda", generator=gen)
+      resets = torch.rand(nsteps, nenvs, device="cuda", generator=gen) < 0.01
+      last = torch.randn(nenvs, device="cuda", generator=gen)
+      for variant, vname in ((1, "direct"), (2, "tma")):
+        if variant == 2 and (nenvs % 16 or nenvs < 32):
+          continue
+        times = []
+        for it in range(8):
+          flush.zero_()
+          s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          s.record()
+          K.gae(rewards, values, resets, last, 0.99, 0.95, False, variant)
+          e.record()
+          torch.cuda.synchronize()
+          if it >= 3:
+            times.append(s.elapsed_time(e))
+        ms = float(np.median(times))
+        gbs = (17.0 * nsteps * nenvs + 4 * nenvs) / ms / 1e6
+        rows.append({"T": nsteps, "N": nenvs, "variant": vname, "ms": ms, "GBps": gbs,
+                     "frac": gbs / hbm_peak})
+  return rows
+
+
+def run_ours(args, rank, world, local):
+  import derl_b200 as d
+  from derl_b200 import _lib, ops
+  d.summary.stop_recording()
+  device = torch.device("cuda", local)
+  torch.cuda.set_device(device)
+  torch.backends.cudnn.benchmark = True
+  tf32 = args.net in ("tf32", "bf16")
+  torch.backends.cudnn.allow_tf32 = tf32
+  torch.backends.cuda.matmul.allow_tf32 = tf32
+
+  torch.manual_seed(0)  # identical initial weights on every rank
+  model = d.NatureCNNModel([args.nactions, 1])
+  if args.net == "bf16":
+    model.autocast_dtype = torch.bfloat16
+  policy = d.ActorCriticPolicy(model)
+  nenvs, horizon = args.envs_per_gpu, args.horizon
+  source = d.SyntheticRolloutRunner(policy, "atari", nenvs, horizon, nsteps=None, device=device,
+                                    seed=1000 + rank, nactions=args.nactions)
+  np.random.seed(1234 + rank)  # local permutations per shard
+  alg, runner = build_alg(args, d, source, world, device)
+  nbatches = args.epochs * args.minibatches
+  samples_per_step = horizon * nenvs * args.epochs * world
+  hbm_peak, peak_kind = peaks()
+
+  # ---- value: rollout resident in HBM
+  sec0, _ = timed_updates(alg, runner, nbatches, 0, args.warmup, world, False)  # warm-up only
+  ops.PROFILE = []
+  launches0 = _lib.launch_count()
+  with ClockSampler(local) as clocks:
+    sec, losses = timed_updates(alg, runner, nbatches, args.steps, 0, world, False)
+  launches = _lib.launch_count() - launches0
+  ktimes = kernel_times(ops.PROFILE)
+  ops.PROFILE = None
+  value = samples_per_step * args.steps / sec
+  last_loss = float(losses[-1])
+
+  # ---- roofline of the dominant hand-written kernel (TMA row gather)
+  mb_rows = horizon * nenvs // args.minibatches
+  roofline, kernels = None, {}
+  if "gather_rows" in ktimes:
+    n, ms = ktimes["gather_rows"]
+    bytes_per_launch = (8 + 2 * OBS_ROW_BYTES) * mb_rows
+    achieved = bytes_per_launch / ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "gather_rows_tma_kernel", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
+                "launch_ms": ms, "launches_timed": n}
+  per_elem = {"gae": 17.0 * horizon * nenvs + 4 * nenvs,
+              "ppo_loss_categorical": (8 * args.nactions + 32) * min(args.micro_batch, mb_rows),
+              "gather_columns": (8 + 2 * (8 + 4 + 4 + 4 + 4 + 4 + 1)) * mb_rows,
+              "normalize": 8.0 * mb_rows}
+  for name, (n, ms) in ktimes.items():
+    entry = {"launches": n, "mean_ms": ms}
+    if name in per_elem:
+      entry["GBps"] = per_elem[name] / ms / 1e6
+      entry["frac"] = entry["GBps"] / hbm_peak
+    kernels[name] = entry
+
+  # ---- e2e: rollout in pinned host memory, uploaded inside the timed region
+  e2e = None
+  import psutil
+  host_need = world * (horizon + 1) * nenvs * (OBS_ROW_BYTES + 32)
+  if not args.no_e2e and psutil.virtual_memory().available < 2 * host_need:
+    e2e = {"value": None, "unit": "samples/s", "skipped": "not enough free host RAM for the "
+           f"pinned rollouts ({host_need >> 30} GiB needed)"}
+  elif not args.no_e2e:
+    host_source = HostRolloutSource(policy, source.rollout(), nenvs, horizon)
+    source._cached = None
+    torch.cuda.empty_cache()
+    alg_h, runner_h = build_alg(args, d, host_source, world, device)
+    sec_h, _ = timed_updates(alg_h, runner_h, nbatches, args.steps, 1, world, True)
+    perm_bytes = args.epochs * horizon * nenvs * 8
+    e2e = {"value": samples_per_step * args.steps / sec_h, "unit": "samples/s",
+           "h2d_bytes_per_step": host_source.bytes + perm_bytes,
+           "d2h_bytes_per_step": nenvs * 4 + nbatches * 4, "ms_per_step": sec_h / args.steps * 1e3}
+    del host_source, alg_h, runner_h
+
+  sweep = gae_sweep(d, hbm_peak) if (args.gae_sweep and rank == 0) else None
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    v, s = cpu_update_throughput(args, args.cpu_envs, 1, 1)
+    cpu = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": (f"{args.cpu_envs} envs x {horizon} steps, {args.epochs} epochs x "
+                      f"{args.minibatches} minibatches, NatureCNN fp32 full update, "
+                      f"{s:.1f} s per step, 1 warm-up + 1 timed")}
+
+  if rank == 0:
+    line = {
+        "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": {"tf32": "f32 params, tf32 tensor-core conv/GEMM; GAE f64 registers; u8 gather",
+                  "fp32": "f32; GAE f64 registers; u8 gather",
+                  "bf16": "f32 params, bf16 autocast network; GAE f64 registers; u8 gather"}[args.net],
+        "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+        "last_loss": last_loss,
+    }
+    if sweep is not None:
+      line["gae_sweep"] = sweep
+    print(json.dumps(line), flush=True)
+
+
+def main():
+  args = parse_args()
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.impl == "reference":
+    run_reference(args, rank)
+    return
+  if world > 1:
+    from derl_b200 import parallel
+    parallel.init_from_env("nccl")
+  run_ours(args, rank, world, local)
+  if world > 1:
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

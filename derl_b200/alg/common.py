@@ -53,14 +53,33 @@ class Loss(ABC):
     """Computes and returns loss value on given data."""
 
 
-class Trainer:
-  """loss -> zero_grad -> backward -> [grad_sync] -> clip -> anneal -> optimizer.step."""
+def _split_rows(data, size):
+  """Row chunks of a minibatch dict ("state" passes through), for gradient accumulation."""
+  nrows = data["observations"].shape[0]
+  for lo in range(0, nrows, size):
+    yield {k: (v if k == "state" else v[lo:lo + size]) for k, v in data.items()}, \
+        min(size, nrows - lo) / nrows
 
-  def __init__(self, optimizer, anneals=None, max_grad_norm=None, grad_sync=None):
+
+class Trainer:
+  """loss -> zero_grad -> backward -> [grad_sync] -> clip -> anneal -> optimizer.step.
+
+  Extensions over the reference (both default to the reference's behaviour):
+    grad_sync    callable(model) run right after backward (NCCL gradient all-reduce);
+    micro_batch  rows per forward/backward pass: a minibatch larger than this is processed
+                 in row chunks whose losses are weighted by their share of the minibatch, so
+                 the accumulated gradient equals the full-minibatch mean's gradient while
+                 activation memory stays bounded (131072 x 84x84x4 frames do not fit one
+                 cuDNN call).  The returned loss is the weighted sum (== the minibatch mean).
+  """
+
+  def __init__(self, optimizer, anneals=None, max_grad_norm=None, grad_sync=None,
+               micro_batch=None):
     self.optimizer = optimizer
     self.anneals = anneals or []
     self.max_grad_norm = max_grad_norm
     self.grad_sync = grad_sync
+    self.micro_batch = micro_batch
     self.step_count = 0
 
   def preprocess_gradients(self, parameters, tag):
@@ -73,11 +92,25 @@ class Trainer:
         grad_norm = total_norm(p.grad for p in parameters if p.grad is not None)
       summary.add_scalar(tag, grad_norm, global_step=self.step_count)
 
-  def step(self, alg, data):
-    loss = alg.loss(data)
+  def _backward(self, alg, data):
+    nrows = data["observations"].shape[0] if "observations" in data else 0
     # a flat gradient buffer (grad_sync) must keep its views alive: zero in place then
-    self.optimizer.zero_grad(set_to_none=self.grad_sync is None)
-    loss.backward()
+    keep_buffers = self.grad_sync is not None
+    if not self.micro_batch or nrows <= self.micro_batch:
+      loss = alg.loss(data)
+      self.optimizer.zero_grad(set_to_none=not keep_buffers)
+      loss.backward()
+      return loss
+    self.optimizer.zero_grad(set_to_none=not keep_buffers)
+    total = None
+    for chunk, weight in _split_rows(data, self.micro_batch):
+      part = alg.loss(chunk) * weight
+      part.backward()
+      total = part.detach() if total is None else total + part.detach()
+    return total
+
+  def step(self, alg, data):
+    loss = self._backward(alg, data)
     if self.grad_sync is not None:
       self.grad_sync(alg.model)
     self.preprocess_gradients(alg.model.parameters(), f"{alg.name}/grad_norm")

@@ -103,13 +103,19 @@ class NatureCNNModel(nn.Module):
     self.init_fn = init_fn
     if init_fn:
       self.apply(init_fn)
+    self.autocast_dtype = None  # e.g. torch.bfloat16: run trunk + heads under autocast
     self.to(_device())
     if next(self.parameters()).is_cuda:
       self.to(memory_format=torch.channels_last)
 
   def _forward(self, observations):
-    hidden = self.base(observations)
-    outputs = [layer(hidden) for layer in self.output_layers]
+    if self.autocast_dtype is not None:
+      with torch.autocast("cuda", dtype=self.autocast_dtype):
+        hidden = self.base(observations)
+        outputs = [layer(hidden).float() for layer in self.output_layers]
+    else:
+      hidden = self.base(observations)
+      outputs = [layer(hidden) for layer in self.output_layers]
     return outputs[0] if self.single_output else outputs
 
   def forward(self, *inputs):

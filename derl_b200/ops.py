@@ -37,20 +37,34 @@ def _dense(t, name, dtypes=None):
   return t
 
 
+# When set to a list, every library call appends (kernel name, start event, end event)
+# recorded on the launching stream: bench.py reads per-kernel device times from it.
+PROFILE = None
+
+
 class _device_of:
   """Make the tensor's device current for the duration of a library call."""
 
-  def __init__(self, t):
+  def __init__(self, t, name=None):
     self.idx = t.device.index
     self.prev = None
+    self.name = name
+    self.start = None
 
   def __enter__(self):
     cur = torch.cuda.current_device()
     if self.idx is not None and cur != self.idx:
       self.prev = cur
       torch.cuda.set_device(self.idx)
+    if PROFILE is not None and self.name is not None:
+      self.start = torch.cuda.Event(enable_timing=True)
+      self.start.record()
 
   def __exit__(self, *exc):
+    if self.start is not None:
+      end = torch.cuda.Event(enable_timing=True)
+      end.record()
+      PROFILE.append((self.name, self.start, end))
     if self.prev is not None:
       torch.cuda.set_device(self.prev)
 
@@ -82,7 +96,7 @@ def gae(rewards: Tensor, values: Tensor, resets: Tensor, last_value: Tensor, gam
   else:
     stats = torch.empty(0, dtype=torch.float64, device=values.device)
     ws_bytes, ws = 0, None
-  with _device_of(values):
+  with _device_of(values, "gae"):
     _lib.check(lib.derl_b200_gae(_p(rewards), int(rewards.dtype == torch.float64), _p(values),
                                  _p(resets), _p(last_value), nsteps, nenvs, float(gamma),
                                  float(lambda_), _p(adv), _p(targets), _p(stats), _p(ws),
@@ -105,7 +119,7 @@ def moments(x: Tensor) -> Tensor:
   stats = torch.empty(3, dtype=torch.float64, device=x.device)
   ws_bytes = lib.derl_b200_moments_workspace_bytes(x.numel())
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-  with _device_of(x):
+  with _device_of(x, "moments"):
     _lib.check(lib.derl_b200_moments(_p(x), x.numel(), _p(stats), _p(ws), ws_bytes, _stream(x)),
                "moments")
   return stats
@@ -123,7 +137,7 @@ def normalize(x: Tensor, stats: Tensor, epsilon: float) -> Tensor:
   _dense(stats, "stats", (torch.float64,))
   _need(stats.numel() >= 3 and x.numel() >= 1, "normalize: bad stats or empty input")
   out = torch.empty_like(x)
-  with _device_of(x):
+  with _device_of(x, "normalize"):
     _lib.check(_lib.load().derl_b200_normalize(_p(x), _p(out), x.numel(), _p(stats),
                                                float(epsilon), _stream(x)), "normalize")
   return out
@@ -147,7 +161,7 @@ def gather_rows(src: Tensor, perm: Tensor, start: int, count: int) -> Tensor:
   row_bytes = src[0].numel() * src.element_size()
   if count == 0 or row_bytes == 0:
     return out
-  with _device_of(src):
+  with _device_of(src, "gather_rows"):
     _lib.check(_lib.load().derl_b200_gather_rows(_p(src), src.shape[0], row_bytes, _p(perm),
                                                  start, count, _p(out), _stream(src)),
                "gather_rows")
@@ -191,7 +205,7 @@ def gather_columns(columns: List[Tensor], perm: Tensor, start: int, count: int,
     srcs = (_VP * ncol)(*[c.data_ptr() for c in columns])
     dsts = (_VP * ncol)(*[o.data_ptr() for o in outs])
     rbs = (ctypes.c_int64 * ncol)(*row_bytes)
-    with _device_of(columns[0]):
+    with _device_of(columns[0], "gather_columns"):
       _lib.check(lib.derl_b200_gather_columns(ncol, srcs, rbs, dsts, _p(perm), start, count,
                                               int(moments_col), _p(stats), _p(ws), ws_bytes,
                                               _stream(columns[0])), "gather_columns")
@@ -256,7 +270,7 @@ def ppo_loss_categorical(logits: Optional[Tensor], values: Optional[Tensor],
   lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
   dlogits = torch.empty_like(logits) if logits is not None else ref.new_empty(0)
   dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
-  with _device_of(ref):
+  with _device_of(ref, "ppo_loss_categorical"):
     _lib.check(lib.derl_b200_ppo_loss_categorical(
         _p(logits), nb, nact, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
         _p(value_targets), _p(old_values), int(cliprange is not None),
@@ -316,7 +330,7 @@ def ppo_loss_gaussian(loc: Optional[Tensor], scale: Optional[Tensor], values: Op
   dloc = torch.empty_like(loc) if loc is not None else ref.new_empty(0)
   dscale = torch.empty_like(scale) if loc is not None else ref.new_empty(0)
   dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
-  with _device_of(ref):
+  with _device_of(ref, "ppo_loss_gaussian"):
     _lib.check(lib.derl_b200_ppo_loss_gaussian(
         _p(loc), _p(scale), nb, ndim, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
         _p(value_targets), _p(old_values), int(cliprange is not None), float(cliprange or 0.),

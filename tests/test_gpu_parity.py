@@ -1,0 +1,558 @@
+"""Parity tests proper: the CUDA path (through torch.ops.derl_b200 -> ctypes -> C ABI) against
+the oracle and the committed golden vectors.  Integer / byte / index work is bit-exact; GAE
+is bit-exact; float32 loss terms within the tolerance stated at each assert (north_star:
+fp32 relative 1e-5).  Run on a B200: `pytest -m gpu`."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import derl_b200 as d
+from derl_b200 import _lib
+from oracle import derl_oracle as O
+
+pytestmark = pytest.mark.gpu
+K = torch.ops.derl_b200
+DEV = "cuda"
+
+
+def cuda(x):
+  return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def run_gae(rewards, values, resets, last_value, gamma, lambda_, variant=0, want_stats=False):
+  nsteps = values.shape[0]
+  adv, vt, stats = K.gae(cuda(rewards).reshape(nsteps, -1), cuda(values).reshape(nsteps, -1),
+                         cuda(resets).reshape(nsteps, -1), cuda(last_value).reshape(-1),
+                         gamma, lambda_, want_stats, variant)
+  return adv.cpu().numpy(), vt.cpu().numpy(), stats.cpu().numpy()
+
+
+def variants_for(nenvs):
+  return (0, 1, 2) if nenvs % 16 == 0 and nenvs >= 32 else (0, 1)
+
+
+class ConstPolicy:
+  def __init__(self, last_value, model=None):
+    self.last_value, self.model = last_value, model
+
+  def act(self, inputs, state=None, update_state=True, training=False):
+    return {"values": self.last_value}
+
+  def is_recurrent(self):
+    return False
+
+
+# =============================================================================== K1: GAE
+def test_device_is_sm100_and_library_sees_it():
+  assert torch.cuda.get_device_capability()[0] == 10
+  assert _lib.load().derl_b200_device_ok() == 0
+
+
+def test_gae_golden_vectors_bit_exact(golden):
+  g = golden("live_gae.npz")
+  for i in range(g.ncases):
+    c = g.case(i)
+    norm = {-1: None, 0: False, 1: True}[int(c["normalize"])]
+    nsteps = c["values"].shape[0]
+    nenvs = c["values"].size // nsteps
+    for variant in variants_for(nenvs):
+      traj = dict(rewards=c["rewards"], values=c["values"], resets=c["resets"],
+                  state=dict(latest_observations=None))
+      gae = d.GAE(ConstPolicy(c["last_value"]), gamma=float(c["gamma"]),
+                  lambda_=float(c["lambda_"]), normalize=norm, variant=variant)
+      adv, vt = gae(traj)
+      assert isinstance(adv, np.ndarray) and adv.dtype == np.float32  # NumPy in -> NumPy out
+      assert adv.shape == c["advantages"].shape and vt.shape == c["value_targets"].shape
+      np.testing.assert_array_equal(vt, c["value_targets"], err_msg=f"case {i} v{variant}")
+      normalized = norm or (norm is None and adv.size > 1)
+      if not normalized:
+        np.testing.assert_array_equal(adv, c["advantages"], err_msg=f"case {i} v{variant}")
+      else:  # float64 device moments vs NumPy's float32 pairwise mean/std: tolerance, not bits
+        scale = np.abs(c["advantages"]).max()
+        np.testing.assert_allclose(adv, c["advantages"], rtol=1e-5, atol=2e-6 * scale)
+      assert traj["advantages"] is adv and traj["value_targets"] is vt
+
+
+def test_gae_reference_fixture(golden):
+  g = golden("ref_a2c_atari_gae.npz")
+  gamma = float(g["gamma"])
+  values = g["values"][..., 0]
+  last_value = ((g["advantages"][-1].astype(np.float64) - (g["rewards"][-1] - values[-1]))
+                / gamma).astype(np.float32)
+  adv, vt, _ = run_gae(g["rewards"], values, g["resets"], last_value, gamma, float(g["lambda_"]))
+  np.testing.assert_array_equal(adv[:-1], g["advantages"][:-1])
+  np.testing.assert_allclose(adv[-1], g["advantages"][-1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("nsteps,nenvs,rdtype,reset_prob", [
+    (128, 4096, np.float32, 0.01),   # config 3
+    (128, 8, np.float64, 0.01),      # config 1
+    (2048, 1, np.float64, 0.001),    # config 2 (unbatched)
+    (512, 1040, np.float64, 0.05),   # N % 16 == 0, not a multiple of 32: ragged last strip
+    (37, 48, np.float32, 0.3),       # T not a multiple of the time tile
+    (1, 64, np.float32, 0.5),        # single step: only the two-rounding last row
+    (15, 33, np.float64, 0.2),       # direct path only
+    (16, 32, np.float32, 1.0),       # every step resets
+    (512, 65536, np.float32, 0.01),  # sweep-sized (570 MB of traffic)
+])
+def test_gae_random_vs_oracle_bit_exact(nsteps, nenvs, rdtype, reset_prob):
+  rng = np.random.RandomState(nsteps * 7 + nenvs)
+  rewards = rng.standard_normal((nsteps, nenvs)).astype(rdtype)
+  values = rng.standard_normal((nsteps, nenvs)).astype(np.float32)
+  resets = rng.random((nsteps, nenvs)) < reset_prob
+  last_value = rng.standard_normal(nenvs).astype(np.float32)
+  want_a, want_vt = O.gae_c(rewards, values, resets, last_value, 0.99, 0.95)
+  for variant in variants_for(nenvs):
+    adv, vt, stats = run_gae(rewards, values, resets, last_value, 0.99, 0.95, variant, True)
+    np.testing.assert_array_equal(adv, want_a, err_msg=f"variant {variant}")
+    np.testing.assert_array_equal(vt, want_vt, err_msg=f"variant {variant}")
+    a64 = want_a.astype(np.float64)
+    np.testing.assert_allclose(stats, [a64.sum(), (a64 * a64).sum(), a64.size], rtol=1e-12)
+
+
+def test_gae_special_values_follow_ieee_like_numpy():
+  """inf / nan / signed zeros propagate exactly as NumPy's float64 arithmetic does."""
+  nsteps, nenvs = 6, 32
+  rng = np.random.RandomState(3)
+  rewards = rng.standard_normal((nsteps, nenvs))
+  values = rng.standard_normal((nsteps, nenvs)).astype(np.float32)
+  resets = rng.random((nsteps, nenvs)) < 0.3
+  rewards[2, 0], values[3, 1], rewards[4, 2] = np.inf, np.nan, -0.0
+  values[4, 2], values[5, 2], resets[4, 2] = 0.0, -1.0, True
+  last_value = rng.standard_normal(nenvs).astype(np.float32)
+  with np.errstate(all="ignore"):
+    want_a, want_vt = O.gae(rewards, values, resets, last_value, 0.99, 0.95, normalize=False)
+  for variant in (1, 2):
+    adv, vt, _ = run_gae(rewards, values, resets, last_value, 0.99, 0.95, variant)
+    np.testing.assert_array_equal(adv.view(np.uint32), want_a.view(np.uint32))
+    np.testing.assert_array_equal(vt.view(np.uint32), want_vt.view(np.uint32))
+
+
+def test_gae_tensor_in_tensor_out_and_unbatched():
+  rng = np.random.RandomState(5)
+  nsteps = 300
+  traj_np = dict(rewards=rng.standard_normal(nsteps), resets=rng.random(nsteps) < .05,
+                 values=rng.standard_normal((nsteps, 1)).astype(np.float32))
+  last_value = rng.standard_normal(1).astype(np.float32)
+  want_a, want_vt = O.gae(traj_np["rewards"], traj_np["values"], traj_np["resets"], last_value,
+                          normalize=False)
+  traj = {k: cuda(v) for k, v in traj_np.items()}
+  traj["state"] = dict(latest_observations=None)
+  adv, vt = d.GAE(ConstPolicy(cuda(last_value)), normalize=False)(traj)
+  assert adv.is_cuda and adv.shape == (nsteps,) and vt.shape == (nsteps, 1)
+  np.testing.assert_array_equal(adv.cpu().numpy(), want_a)
+  np.testing.assert_array_equal(vt.cpu().numpy(), want_vt)
+
+
+def test_gae_host_entry_point_of_the_c_abi():
+  """derl_b200_gae_host called with plain NumPy buffers, as a ctypes binding in the
+  reference's tree would."""
+  lib = _lib.load()
+  rng = np.random.RandomState(9)
+  nsteps, nenvs = 64, 96
+  rewards = rng.standard_normal((nsteps, nenvs))
+  values = rng.standard_normal((nsteps, nenvs)).astype(np.float32)
+  resets = (rng.random((nsteps, nenvs)) < .1).astype(np.uint8)
+  last_value = rng.standard_normal(nenvs).astype(np.float32)
+  adv, vt = np.empty_like(values), np.empty_like(values)
+  ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+  for normalize in (0, 1):
+    rc = lib.derl_b200_gae_host(ptr(rewards), 1, ptr(values), ptr(resets), ptr(last_value),
+                                nsteps, nenvs, 0.99, 0.95, normalize, 1e-8, ptr(adv), ptr(vt),
+                                None)
+    _lib.check(rc, "gae_host")
+    want_a, want_vt = O.gae(rewards, values, resets.astype(bool), last_value, 0.99, 0.95,
+                            normalize=bool(normalize))
+    np.testing.assert_array_equal(vt, want_vt)
+    if normalize:
+      np.testing.assert_allclose(adv, want_a, rtol=1e-5, atol=1e-5)
+    else:
+      np.testing.assert_array_equal(adv, want_a)
+
+
+def test_moments_and_normalize_vs_numpy():
+  rng = np.random.RandomState(11)
+  for n in (1, 2, 255, 4097, 1 << 20):
+    x = (rng.standard_normal(n) * 3 + 0.7).astype(np.float32)
+    stats = K.moments(cuda(x))
+    x64 = x.astype(np.float64)
+    np.testing.assert_allclose(stats.cpu().numpy(), [x64.sum(), (x64 * x64).sum(), n], rtol=1e-12)
+    if n > 1:
+      out = K.normalize(cuda(x), stats, 1e-8).cpu().numpy()
+      want = O.normalize_advantages(x)
+      # float64 device moments vs NumPy float32 pairwise mean/std -> agree to ~1 ulp of the scale
+      np.testing.assert_allclose(out, want, rtol=1e-5, atol=2e-6)
+      assert abs(out.mean()) < 1e-5 and abs(out.std() - 1) < 1e-4
+
+
+# =============================================================================== K2: gather
+@pytest.mark.parametrize("row_shape,dtype,nrows", [
+    ((84, 84, 4), np.uint8, 300),      # frame stacks: TMA bulk path, 28224-B rows
+    ((2048,), np.uint8, 257),          # smallest row on the TMA path
+    ((65536 + 16,), np.uint8, 40),     # rows wider than one stage: 3 chunks
+    ((28672 * 2,), np.uint8, 33),      # exactly two full stages
+    ((17,), np.float64, 1000),         # MuJoCo observations: 136-B rows, vector path
+    ((6,), np.float32, 999),           # actions [B, 6]
+    ((3,), np.uint8, 500),             # odd byte rows
+    ((2047,), np.uint8, 129),          # unaligned wide rows: byte path
+    ((), np.int64, 4096),              # scalar column
+])
+def test_gather_rows_bit_exact(row_shape, dtype, nrows):
+  rng = np.random.RandomState(nrows)
+  if np.issubdtype(dtype, np.integer):
+    src = rng.randint(0, 255, (nrows,) + row_shape).astype(dtype)
+  else:
+    src = rng.standard_normal((nrows,) + row_shape).astype(dtype)
+  perm = rng.permutation(nrows).astype(np.int64)
+  src_d, perm_d = cuda(src), cuda(perm)
+  for start, count in ((0, nrows), (0, 1), (nrows - 1, 1), (nrows // 3, nrows // 2), (5, 0)):
+    out = K.gather_rows(src_d, perm_d, start, count).cpu().numpy()
+    np.testing.assert_array_equal(out, src[perm[start:start + count]])
+    np.testing.assert_array_equal(out, O.gather_rows_c(src, perm, start, count))
+  # repeated indices are legal for an index gather (Take), not only permutations
+  idx = rng.randint(0, nrows, 2 * nrows).astype(np.int64)
+  out = K.gather_rows(src_d, cuda(idx), 0, idx.size).cpu().numpy()
+  np.testing.assert_array_equal(out, src[idx])
+
+
+def test_gather_columns_bit_exact_with_fused_moments():
+  rng = np.random.RandomState(21)
+  n = 5000
+  cols = dict(actions=rng.randint(0, 18, n).astype(np.int64),
+              log_prob=rng.standard_normal(n).astype(np.float32),
+              advantages=(rng.standard_normal(n) * 2 + .3).astype(np.float32),
+              value_targets=rng.standard_normal((n, 1)).astype(np.float32),
+              values=rng.standard_normal((n, 1)).astype(np.float32),
+              rewards=rng.standard_normal(n), resets=rng.random(n) < .1,
+              cont_actions=rng.standard_normal((n, 6)).astype(np.float32),
+              odd=rng.randint(0, 255, (n, 3)).astype(np.uint8),
+              half=rng.standard_normal((n, 5)).astype(np.float16))
+  keys = list(cols)
+  perm = rng.permutation(n).astype(np.int64)
+  dev = [cuda(cols[k]) for k in keys]
+  for start, count in ((0, n), (1234, 1250), (n - 1, 1), (0, 0)):
+    *outs, moments = K.gather_columns(dev, cuda(perm), start, count, keys.index("advantages"))
+    rows = perm[start:start + count]
+    for key, out in zip(keys, outs):
+      np.testing.assert_array_equal(out.cpu().numpy(), cols[key][rows], err_msg=key)
+    if count:
+      a = cols["advantages"][rows].astype(np.float64)
+      np.testing.assert_allclose(moments.cpu().numpy(), [a.sum(), (a * a).sum(), count],
+                                 rtol=1e-12)
+  *outs, moments = K.gather_columns(dev[:2], cuda(perm), 0, 100, -1)
+  assert moments.numel() == 0 and len(outs) == 2
+
+
+def test_gather_full_config3_minibatch_against_torch_index():
+  """4096 envs x 128 steps of frame stacks (14.8 GB resident), one 131072-sample minibatch:
+  bit-identical to torch's own advanced indexing, and a gather with the inverse permutation
+  restores the rollout (round trip) on a 1/8 slice."""
+  nsamples = 4096 * 128
+  gen = torch.Generator(device=DEV).manual_seed(0)
+  obs = torch.randint(0, 256, (nsamples, 84, 84, 4), generator=gen, device=DEV,
+                      dtype=torch.uint8)
+  np.random.seed(0)
+  perm = torch.from_numpy(np.random.permutation(nsamples)).to(DEV)
+  mb = nsamples // 4
+  out = K.gather_rows(obs, perm, mb, mb)
+  for lo in range(0, mb, 16384):
+    want = obs[perm[mb + lo:mb + lo + 16384]]
+    assert torch.equal(out[lo:lo + 16384], want)
+  del want
+  inverse = torch.empty_like(perm)
+  inverse[perm[mb:2 * mb]] = torch.arange(mb, device=DEV)
+  # rows perm[mb:2mb] scattered back: out[inverse[r]] == obs[r] for every r in that set
+  some = perm[mb:mb + 65536]
+  back = K.gather_rows(out, inverse[some].contiguous(), 0, some.numel())
+  assert torch.equal(back, obs[some])
+
+
+def test_minibatch_pipeline_matches_reference_golden(golden):
+  """TransformInteractions[GAE, MergeTimeBatch] -> IterateWithMinibatches ->
+  TransformInteractions[NormalizeAdvantages] under np.random.seed: same rows in every
+  minibatch as the reference selected (ids bit-exact, ragged tails included)."""
+  g = golden("live_minibatches.npz")
+  for i in range(g.ncases):
+    c = g.case(i)
+    nsteps, nenvs = c["ids"].shape
+    rollout = {k: c[k] for k in ("observations", "ids", "actions", "log_prob", "values",
+                                 "rewards", "resets")}
+    rollout["state"] = dict(latest_observations=np.zeros((nenvs, 4, 3, 2), np.uint8))
+
+    class Source:
+      env = type("E", (), {"nenvs": nenvs, "unwrapped": property(lambda s: s)})()
+      policy = ConstPolicy(c["last_value"])
+      horizon, step_count = nsteps, 0
+      nsteps = 1
+
+      def run(self, obs=None):
+        yield dict(rollout)
+
+    runner = d.ppo_runner_wrap(Source(), num_epochs=int(c["epochs"]),
+                               num_minibatches=int(c["nmb"]))
+    np.random.seed(int(c["seed"]))
+    flat_obs = c["observations"].reshape((nsteps * nenvs,) + c["observations"].shape[2:])
+    ids, advs, sizes = [], [], []
+    for batch in runner.run():
+      assert list(batch.keys())[:3] == ["observations", "ids", "actions"]
+      rows = batch["ids"].cpu().numpy()
+      np.testing.assert_array_equal(batch["observations"].cpu().numpy(), flat_obs[rows])
+      np.testing.assert_array_equal(batch["resets"].cpu().numpy(), c["resets"].reshape(-1)[rows])
+      ids.append(rows)
+      advs.append(batch["advantages"].cpu().numpy())
+      sizes.append(len(rows))
+    np.testing.assert_array_equal(sizes, c["mb_sizes"])
+    np.testing.assert_array_equal(np.concatenate(ids), c["mb_ids"])
+    # normalisation: float64 moments on device vs NumPy float32 pairwise -> tolerance
+    np.testing.assert_allclose(np.concatenate(advs), c["mb_advantages"], rtol=1e-5, atol=2e-6)
+
+
+def test_iterate_without_shuffle_and_too_many_minibatches():
+  rollout = dict(observations=torch.arange(10, device=DEV).reshape(10, 1).float(),
+                 advantages=torch.arange(10, device=DEV).float(), state=dict(k=1))
+
+  class Source:
+    env, policy, horizon, nsteps, step_count, nenvs = None, None, 10, 10, 0, None
+
+    def run(self, obs=None):
+      yield dict(rollout)
+
+  batches = list(d.IterateWithMinibatches(Source(), 2, 3, shuffle_before_epoch=False).run())
+  assert [b["observations"].shape[0] for b in batches] == [3, 3, 3, 1] * 2
+  assert torch.equal(batches[1]["advantages"], torch.tensor([3., 4., 5.], device=DEV))
+  assert batches[0]["state"] == dict(k=1)
+  with pytest.raises(ValueError):  # range() step 0, as in the reference
+    list(d.IterateWithMinibatches(Source(), 1, 11).run())
+
+
+# =============================================================================== K3: loss
+class HeadPolicy:
+  def __init__(self, head, values):
+    self.head, self.values = head, values
+    self.model = torch.nn.Linear(1, 1).to(DEV)
+
+  def act(self, inputs, state=None, update_state=True, training=False):
+    dist = d.policies.CategoricalHead(*self.head) if len(self.head) == 1 \
+        else d.policies.DiagNormalHead(*self.head)
+    return {"distribution": dist, "values": self.values}
+
+
+def loss_case_inputs(c):
+  head = [cuda(c[f"head{j}"]).requires_grad_() for j in range(2) if f"head{j}" in c]
+  values = cuda(c["pred_values"]).requires_grad_()
+  batch = {k: c[k] for k in ("actions", "log_prob", "advantages", "value_targets", "values")}
+  clip = None if float(c["cliprange"]) < 0 else float(c["cliprange"])
+  return head, values, batch, clip
+
+
+def test_ppo_loss_golden_forward_backward_and_scalars(golden):
+  """Reference PPOLoss + torch autograd outputs (tests/golden/live_ppo_loss.npz).
+  Tolerance: rtol 1e-5 on the loss (north_star); gradients rtol 1e-5 with an absolute floor
+  of 1e-5 * max|grad| for elements that are themselves rounding noise."""
+  g = golden("live_ppo_loss.npz")
+  for i in range(g.ncases):
+    c = g.case(i)
+    head, values, batch, clip = loss_case_inputs(c)
+    fn = d.PPOLoss(HeadPolicy(head, values), cliprange=clip, value_loss_coef=float(c["vcoef"]),
+                   entropy_coef=float(c["ecoef"]))
+    loss = fn(batch)
+    assert loss.shape == () and loss.is_cuda and fn.call_count == 1
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), c["loss"], rtol=1e-5, err_msg=f"case {i}")
+    dv = values.grad.cpu().numpy()
+    np.testing.assert_allclose(dv, c["dvalues"], rtol=1e-5, atol=1e-5 * np.abs(c["dvalues"]).max())
+    for j, h in enumerate(head):
+      want = c[f"dhead{j}"]
+      np.testing.assert_allclose(h.grad.cpu().numpy(), want, rtol=1e-5,
+                                 atol=1e-5 * np.abs(want).max(), err_msg=f"case {i} head{j}")
+    stats = fn.last_stats.cpu().numpy()
+    for key in ("loss", "policy_loss", "entropy", "value_loss", "advantages", "value_targets",
+                "value_preds", "r_squared"):
+      np.testing.assert_allclose(stats[d.alg.ppo.STAT[key]], c[f"log_ppo_{key}"], rtol=2e-5,
+                                 atol=2e-7, err_msg=f"case {i} {key}")
+    # the two partial entry points (policy_loss / value_loss)
+    head2, values2, _, _ = loss_case_inputs(c)
+    fn2 = d.PPOLoss(HeadPolicy(head2, values2), cliprange=clip,
+                    value_loss_coef=float(c["vcoef"]), entropy_coef=float(c["ecoef"]))
+    np.testing.assert_allclose(fn2.policy_loss(batch).item(), c["policy_loss"], rtol=1e-5,
+                               atol=1e-7)
+    np.testing.assert_allclose(fn2.value_loss(batch).item(), c["value_loss"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind,width", [("categorical", 4), ("categorical", 18),
+                                        ("categorical", 130), ("gaussian", 6),
+                                        ("gaussian", 40)])
+def test_ppo_loss_large_batch_vs_oracle(kind, width):
+  """B = 131072 (config-3 minibatch) against the oracle's torch restatement on the CPU and
+  its autograd gradients; also checks run-to-run determinism of the two-stage reduction."""
+  nb = 131072 if width <= 18 else 20000
+  rng = np.random.RandomState(width)
+  batch = dict(log_prob=(rng.standard_normal(nb) * .2 - 1.5).astype(np.float32),
+               advantages=rng.standard_normal(nb).astype(np.float32),
+               value_targets=rng.standard_normal((nb, 1)).astype(np.float32),
+               values=rng.standard_normal((nb, 1)).astype(np.float32))
+  pred = (batch["values"] + rng.standard_normal((nb, 1)) * .15).astype(np.float32)
+  if kind == "categorical":
+    head = [rng.standard_normal((nb, width)).astype(np.float32)]
+    batch["actions"] = rng.randint(0, width, nb).astype(np.int64)
+  else:
+    head = [rng.standard_normal((nb, width)).astype(np.float32),
+            np.exp(rng.standard_normal((nb, width)) * .2).astype(np.float32)]
+    batch["actions"] = (head[0] + .5 * rng.standard_normal((nb, width))).astype(np.float32)
+    batch["log_prob"] = (batch["log_prob"] - width).astype(np.float32)
+  cpu_head = [torch.tensor(h, requires_grad=True) for h in head]
+  cpu_values = torch.tensor(pred, requires_grad=True)
+  want = O.ppo_loss(cpu_head, cpu_values, batch, 0.1, 0.25, 0.01)
+  want.backward()
+  results = []
+  for _ in range(2):
+    dev_head = [cuda(h).requires_grad_() for h in head]
+    dev_values = cuda(pred).requires_grad_()
+    fn = d.PPOLoss(HeadPolicy(dev_head, dev_values), cliprange=0.1, value_loss_coef=0.25,
+                   entropy_coef=0.01)
+    loss = fn(batch)
+    loss.backward()
+    results.append((loss.item(), [h.grad.clone() for h in dev_head], dev_values.grad.clone()))
+  loss_val, dhead, dvalues = results[0]
+  np.testing.assert_allclose(loss_val, want.item(), rtol=1e-5)
+  for got, ref in zip(dhead + [dvalues], [h.grad for h in cpu_head] + [cpu_values.grad]):
+    ref = ref.numpy()
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+  assert results[1][0] == loss_val and torch.equal(results[1][2], dvalues)  # deterministic
+  assert all(torch.equal(a, b) for a, b in zip(results[1][1], dhead))
+
+
+def test_ppo_loss_grad_scales_with_upstream_gradient():
+  rng = np.random.RandomState(1)
+  nb, width = 512, 5
+  logits = cuda(rng.standard_normal((nb, width)).astype(np.float32)).requires_grad_()
+  values = cuda(rng.standard_normal((nb, 1)).astype(np.float32)).requires_grad_()
+  args = (cuda(rng.randint(0, width, nb)), cuda(rng.standard_normal(nb).astype(np.float32)),
+          cuda(rng.standard_normal(nb).astype(np.float32)),
+          cuda(rng.standard_normal((nb, 1)).astype(np.float32)),
+          cuda(rng.standard_normal((nb, 1)).astype(np.float32)))
+  loss, dlogits, dvalues, _ = K.ppo_loss_categorical(logits, values, *args, 0.2, 0.25, 0.01)
+  (3.0 * loss).backward()
+  assert torch.allclose(logits.grad, 3.0 * dlogits) and torch.allclose(values.grad, 3.0 * dvalues)
+
+
+def test_ppo_pybullet_fixture_through_the_product_model(golden):
+  """testdata/ppo/pybullet through derl_b200.MuJoCoModel + PPOLoss on the GPU: loss0 and all
+  13 parameter gradients at the reference's own tolerance (rtol = atol = 1e-5)."""
+  g = golden("ref_ppo_pybullet.npz")
+  torch.manual_seed(0)
+  model = d.MuJoCoModel(26, [6, 1])
+  assert next(model.parameters()).is_cuda
+  torch.backends.cuda.matmul.allow_tf32 = False
+  fn = d.PPOLoss(d.ActorCriticPolicy(model), cliprange=float(g["cliprange"]),
+                 value_loss_coef=float(g["value_loss_coef"]),
+                 entropy_coef=float(g["entropy_coef"]))
+  batch = {k: g[k] for k in ("observations", "actions", "log_prob", "values", "advantages",
+                             "value_targets")}
+  loss = fn(batch)
+  loss.backward()
+  np.testing.assert_allclose(loss.item(), g["loss0"], rtol=1e-5, atol=1e-5)
+  for j, p in enumerate(model.parameters()):
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"grad_{j}"], rtol=1e-5, atol=1e-5,
+                               err_msg=f"grad_{j}")
+
+
+@pytest.mark.parametrize("name,kind", [("live_update_mujoco.npz", "mujoco"),
+                                       ("live_update_atari.npz", "atari")])
+def test_full_ppo_update_matches_reference_losses(golden, name, kind):
+  """Two rollouts through the whole drop-in pipeline (GAE -> minibatches -> normalise ->
+  fused loss -> backward -> clip -> Adam) with the reference's seeds: the sequence of
+  losses the reference's own classes produced.  float32 network on both sides (TF32 off);
+  tolerance 1e-4 relative: GPU-vs-CPU float32 GEMM/conv rounding compounds over Adam steps."""
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.backends.cudnn.allow_tf32 = False
+  g = golden(name)
+  torch.manual_seed(0)
+  if kind == "mujoco":
+    model = d.MuJoCoModel(g["r0_observations"].shape[-1], [g["r0_actions"].shape[-1], 1])
+    nenvs = None
+  else:
+    model = d.NatureCNNModel([4, 1])
+    nenvs = int(g["nenvs"])
+  policy = d.ActorCriticPolicy(model)
+  rollouts = []
+  for r in range(int(g["nrollouts"])):
+    data = {k: g[f"r{r}_{k}"] for k in ("observations", "actions", "log_prob", "values",
+                                         "rewards", "resets")}
+    data["state"] = dict(latest_observations=g[f"r{r}_latest_observations"])
+    rollouts.append(data)
+
+  class Source:
+    env = type("E", (), {"nenvs": nenvs, "unwrapped": property(lambda s: s)})()
+    horizon, nsteps, step_count = 1, 1, 0
+
+    def __init__(self):
+      self.policy = policy
+      self.nenvs = nenvs
+
+    def run(self, obs=None):
+      for data in rollouts:
+        yield dict(data)
+
+  runner = d.ppo_runner_wrap(Source(), num_epochs=int(g["epochs"]),
+                             num_minibatches=int(g["nmb"]))
+  optimizer = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), eps=1e-5)
+  alg = d.PPO(runner, d.Trainer(optimizer, max_grad_norm=.5), cliprange=float(g["cliprange"]),
+              value_loss_coef=float(g["value_loss_coef"]), entropy_coef=float(g["entropy_coef"]))
+  np.random.seed(int(g["seed"]))
+  losses = [alg.step(batch).item() for batch in runner.run()]
+  np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
+  final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+  np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-5)
+  torch.backends.cudnn.allow_tf32 = True
+
+
+# =============================================================================== plumbing
+def test_ops_are_cuda_graph_capturable():
+  """GAE + gather + loss captured once and replayed on new data in the same buffers."""
+  rng = np.random.RandomState(2)
+  nsteps, nenvs, nact = 32, 64, 4
+  size = nsteps * nenvs
+  rewards = cuda(rng.standard_normal((nsteps, nenvs)).astype(np.float32))
+  values = cuda(rng.standard_normal((nsteps, nenvs)).astype(np.float32))
+  resets = cuda(rng.random((nsteps, nenvs)) < .1)
+  last_value = cuda(rng.standard_normal(nenvs).astype(np.float32))
+  logits = cuda(rng.standard_normal((size, nact)).astype(np.float32))
+  actions = cuda(rng.randint(0, nact, size))
+  old_lp = cuda((rng.standard_normal(size) * .1 - 1.4).astype(np.float32))
+  perm = cuda(rng.permutation(size))
+
+  def step():
+    adv, vt, _ = K.gae(rewards, values, resets, last_value, 0.99, 0.95, False, 0)
+    *cols, moments = K.gather_columns([adv.reshape(-1), vt.reshape(-1), values.reshape(-1),
+                                       old_lp, actions], perm, 0, size, 0)
+    nadv = K.normalize(cols[0], moments, 1e-8)
+    lg = K.gather_rows(logits, perm, 0, size)
+    return K.ppo_loss_categorical(lg, cols[2].clone(), cols[4], cols[3], nadv, cols[1], cols[2],
+                                  0.1, 0.25, 0.01)
+
+  stream = torch.cuda.Stream()
+  stream.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(stream):
+    for _ in range(2):
+      eager = step()
+  torch.cuda.current_stream().wait_stream(stream)
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    captured = step()
+  graph.replay()
+  torch.cuda.synchronize()
+  assert captured[0].item() == eager[0].item() and torch.equal(captured[1], eager[1])
+  rewards.add_(1.0)  # new data, same buffers
+  want = step()
+  graph.replay()
+  torch.cuda.synchronize()
+  assert captured[0].item() == want[0].item() and torch.equal(captured[1], want[1])
+
+
+def test_launch_counter_counts_our_kernels():
+  before = _lib.launch_count()
+  K.moments(torch.ones(100, device=DEV))
+  assert _lib.launch_count() == before + 1

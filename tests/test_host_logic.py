@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference interface: wrappers, errors, schedules, models.  CPU."""
+import numpy as np
+import pytest
+import torch
+
+import derl_b200 as d
+from derl_b200.runners.env_runner import RunnerWrapper
+
+
+class Source:
+  def __init__(self):
+    self.env, self.policy, self.horizon, self.nsteps = "env", "policy", 5, 100
+    self.step_count, self.nenvs, self.secret = 7, 3, "hidden"
+
+  def is_exhausted(self):
+    return False
+
+  def __len__(self):
+    return 100
+
+  def run(self, obs=None):
+    yield {}
+
+
+class Passthrough(RunnerWrapper):
+  def run(self, obs=None):
+    yield from self.runner.run(obs)
+
+
+def test_runner_wrapper_proxies_only_the_whitelist():
+  w = Passthrough(Passthrough(Source()))
+  assert (w.env, w.policy, w.horizon, w.nsteps, w.step_count, w.nenvs) == \
+      ("env", "policy", 5, 100, 7, 3)
+  assert w.is_exhausted() is False and len(w) == 100
+  assert isinstance(w.unwrapped, Source)
+  with pytest.raises(AttributeError, match="has no attribute 'secret'"):
+    w.secret
+
+
+def test_gae_errors_come_before_any_kernel():
+  gae = d.GAE(policy=None)
+  z = np.zeros((4, 2), np.float32)
+  with pytest.raises(ValueError, match="cannot contain 'advantages'"):
+    gae(dict(advantages=z))
+  with pytest.raises(ValueError, match="cannot contain 'value_targets'"):
+    gae(dict(value_targets=z))
+  with pytest.raises(ValueError, match="or have last dimension of size 1"):
+    gae(dict(rewards=z, resets=z > 0, values=np.zeros((4, 2, 2), np.float32)))
+  with pytest.raises(ValueError, match="or have last dimension of size 1"):
+    gae(dict(rewards=z, resets=z > 0, values=np.zeros((4,), np.float32)))
+
+
+def test_merge_time_batch_is_a_view():
+  traj = dict(resets=torch.zeros(4, 3, dtype=torch.bool), observations=torch.zeros(4, 3, 5, 2),
+              values=np.zeros((4, 3, 1), np.float32), state=dict(x=1))
+  d.MergeTimeBatch()(traj)
+  assert traj["observations"].shape == (12, 5, 2) and traj["values"].shape == (12, 1)
+  assert traj["resets"].shape == (12,) and traj["state"] == dict(x=1)
+  with pytest.raises(AssertionError):
+    d.MergeTimeBatch()(dict(resets=torch.zeros(4)))
+
+
+def test_linear_anneal_closed_form_equals_stepwise_loop():
+  for start, end, nsteps in ((2.5e-4, 0., 1000), (1., 3., 50), (0.1, 0.1, 10)):
+    fast = d.LinearAnneal(start, nsteps, end)
+    for target in (0, 1, 17, 500, 1000, 1500):
+      fast.step_to(target)
+      # the reference's per-step update (derl/anneal.py:77-86), iterated `target` times
+      value = start
+      for count in range(1, target + 1):
+        value = min(max(start + (end - start) * (count / nsteps), min(start, end)),
+                    max(start, end))
+      assert fast.step_count == target
+      np.testing.assert_allclose(float(fast.get_tensor()), np.float32(value), rtol=1e-7)
+    with pytest.raises(ValueError, match="cannot be smaller"):
+      fast.step_to(3)
+  shared = d.LinearAnneal(1e-3, 10)
+  tensor = shared.get_tensor()
+  shared.step()
+  assert float(tensor) == pytest.approx(9e-4)  # in place: the optimizer keeps seeing it
+
+
+def test_summary_gate_contract():
+  s = d.summary
+  s.start_recording()
+  assert s.should_record()
+  s.set_writer(None)
+  with pytest.raises(ValueError, match="summary.writer cannot be None"):
+    s.add_scalar("a", 1.0)
+  seen = []
+
+  class W:
+    def add_scalar(self, *a, **k):
+      seen.append((a, k))
+  s.set_writer(W())
+  s.add_scalar("tag", 2.0, global_step=3)
+  assert seen == [(("tag", 2.0), dict(global_step=3))]
+  s.set_recording(False)
+  assert not s.should_record()
+  s.set_writer(None)
+
+
+def test_policy_known_answers_from_reference_tests():
+  """derl/policies_test.py:11-29 constants (seed 0, CPU): Gaussian head reproduces actions,
+  log-prob and value; categorical head reproduces value and the log-prob of action 3 (the
+  sampled action itself depends on torch's multinomial stream, which changed after 1.5)."""
+  torch.manual_seed(0)
+  model = d.MuJoCoModel(3, (2, 1)).to("cpu")
+  act = d.ActorCriticPolicy(model).act(torch.randn(3))
+  assert list(act.keys()) == ["actions", "log_prob", "values"]
+  np.testing.assert_allclose(act["actions"], [-1.7938228, 1.0464325], rtol=1e-6)
+  np.testing.assert_allclose(act["log_prob"], -3.7467263, rtol=1e-6)
+  np.testing.assert_allclose(act["values"], [-0.18482158], rtol=1e-6)
+
+  torch.manual_seed(0)
+  model = d.NatureCNNModel((6, 1)).to("cpu")
+  policy = d.ActorCriticPolicy(model)
+  obs = torch.rand(84, 84, 4)
+  out = policy.act({"observations": obs}, training=True)
+  np.testing.assert_allclose(out["values"].detach().numpy(), [0.257305294], rtol=1e-5)
+  logp3 = out["distribution"].log_prob(torch.tensor(3))
+  np.testing.assert_allclose(float(logp3), -1.80754196, rtol=1e-5)
+
+
+def test_model_state_dict_layout():
+  cnn = d.NatureCNNModel([4, 1]).to("cpu")
+  keys = list(cnn.state_dict())
+  assert keys == ["base.conv-0.weight", "base.conv-0.bias", "base.conv-1.weight",
+                  "base.conv-1.bias", "base.conv-2.weight", "base.conv-2.bias",
+                  "base.linear.weight", "base.linear.bias", "output_layers.0.weight",
+                  "output_layers.0.bias", "output_layers.1.weight", "output_layers.1.bias"]
+  assert sum(p.numel() for p in cnn.parameters()) == 1686693
+  mlp = d.MuJoCoModel(17, [6, 1]).to("cpu")
+  assert next(iter(mlp.state_dict())) == "logstd"
+  assert sum(p.numel() for p in mlp.parameters()) == 11085
+  loc, std, values = mlp(torch.zeros(5, 17))
+  assert loc.shape == (5, 6) and std.shape == (5, 6) and values.shape == (5, 1)
+  loc1, std1, v1 = mlp(torch.zeros(17))
+  assert loc1.shape == (6,) and v1.shape == (1,)
+  assert torch.all(cnn.output_layers[0].bias == 0)
+  w = cnn.base[0].weight.detach().reshape(32, -1)
+  np.testing.assert_allclose((w @ w.T).numpy(), np.eye(32), atol=1e-5)  # orthogonal rows
+
+
+def test_ppo_loss_value_errors_before_dispatch():
+  model = d.MuJoCoModel(3, [2, 1]).to("cpu")
+  loss = d.PPOLoss(d.ActorCriticPolicy(model))
+  assert loss.name == "ppo" and loss.call_count == 0
+  obs = np.zeros((4, 3))
+  base = dict(observations=obs, actions=np.zeros((4, 2), np.float32),
+              log_prob=np.zeros(4, np.float32), values=np.zeros((4, 1), np.float32))
+  with pytest.raises(ValueError, match="does not contain 'advantages'"):
+    loss.policy_loss(dict(base))
+  with pytest.raises(ValueError, match="does not contain 'value_targets'"):
+    loss.value_loss(dict(base, advantages=np.zeros(4, np.float32)))
+  with pytest.raises(ValueError, match="mismatched shapes"):
+    loss.policy_loss(dict(base, advantages=np.zeros((4, 1), np.float32)))
+  with pytest.raises(ValueError, match="mismatched shapes"):
+    loss.value_loss(dict(base, value_targets=np.zeros(4, np.float32)))
+
+
+def test_minibatch_iterator_requires_resident_rollout():
+  class OneShot(Source):
+    def run(self, obs=None):
+      yield dict(observations=np.zeros((8, 2)), state={})
+  it = d.IterateWithMinibatches(OneShot(), num_epochs=1, num_minibatches=2)
+  with pytest.raises(TypeError, match="resident on the GPU"):
+    next(it.run())
+
+
+def test_synthetic_rollout_shapes_match_env_runner_layout():
+  r = d.make_rollout("atari", 4, 3, device="cpu", seed=1)
+  assert r["observations"].shape == (4, 3, 84, 84, 4) and r["observations"].dtype == np.uint8
+  assert r["actions"].dtype == np.int64 and r["values"].shape == (4, 3, 1)
+  assert r["rewards"].dtype == np.float64 and set(np.unique(r["rewards"])) <= {-1., 0., 1.}
+  assert r["resets"].dtype == np.bool_ and r["state"]["latest_observations"].shape == (3, 84, 84, 4)
+  m = d.make_rollout("mujoco", 16, None, device="cpu", seed=1)
+  assert m["observations"].shape == (16, 17) and m["observations"].dtype == np.float64
+  assert m["actions"].shape == (16, 6) and m["values"].shape == (16, 1)
+  assert m["rewards"].shape == (16,) and m["state"]["latest_observations"].shape == (17,)
+  src = d.SyntheticRolloutRunner(policy=None, kind="mujoco", nenvs=None, horizon=16, nsteps=32,
+                                 device="cpu")
+  assert len(list(src.run())) == 2 and src.step_count == 32 and src.is_exhausted()
