@@ -12,10 +12,12 @@
 //
 // Two variants compute identical bits:
 //   DIRECT  any shape; register double-buffered coalesced global loads.
-//   TMA     N % 16 == 0; each warp owns a 32-env strip, [TT x 32] tiles of rewards /
+//   TMA     N % 16 == 0; each warp owns a 32- or 64-env strip, [TT x W] tiles of rewards /
 //           values / resets are staged through shared memory by cp.async.bulk.tensor
 //           with an mbarrier ring, outputs leave through TMA stores.
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
+
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -138,11 +140,18 @@ gae_direct_kernel(const RT* __restrict__ rewards, const float* __restrict__ valu
 }
 
 // ------------------------------------------------------------------ TMA variant
-constexpr int kStripW = 32;  // envs per warp strip == lanes
+// One warp per CTA owns a strip of W = 32*E envs (E independent chains per lane for ILP).
+// Time is walked top-down in chunks of TT steps; each chunk's [TT x W] tiles of rewards /
+// values / resets arrive by 2-D TMA into an S-stage mbarrier ring, results leave through a
+// double-buffered pair of output tiles and TMA stores.  Interior chunks run a branch-free
+// body: everything that does not depend on A[t+1] (conversions, delta_t, k_t) is computed
+// for all TT steps first, so the serial chain per step is DMUL -> DADD -> F2F -> F2F only.
+constexpr int kLanes = 32;
 
-template <typename RT, int TT, int S>
+template <typename RT, int TT, int S, int E, int NW>
 struct GaeTmaSmem {
-  static constexpr int kTile = TT * kStripW;
+  static constexpr int kW = kLanes * E * NW;
+  static constexpr int kTile = TT * kW;
   static constexpr size_t r_off = 0;
   static constexpr size_t v_off = r_off + sizeof(RT) * S * kTile;
   static constexpr size_t a_off = v_off + sizeof(float) * S * kTile;
@@ -153,13 +162,23 @@ struct GaeTmaSmem {
   static constexpr uint32_t stage_tx = kTile * (sizeof(RT) + sizeof(float) + 1);
 };
 
-template <typename RT, int TT, int S>
-__global__ void __launch_bounds__(kStripW)
+template <int NW>
+__device__ __forceinline__ void strip_sync() {
+  if constexpr (NW == 1) {
+    __syncwarp();
+  } else {
+    __syncthreads();
+  }
+}
+
+template <typename RT, int TT, int S, int E, int NW, bool kStats>
+__global__ void __launch_bounds__(kLanes * NW)
 gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_v,
                const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_a,
                const __grid_constant__ CUtensorMap tm_vt, const float* __restrict__ last_value,
                int T, int N, double gamma, double gamma_lambda, void* workspace, double* stats) {
-  using L = GaeTmaSmem<RT, TT, S>;
+  using L = GaeTmaSmem<RT, TT, S, E, NW>;
+  constexpr int W = L::kW;
   extern __shared__ __align__(128) uint8_t smem[];
   RT* sr = reinterpret_cast<RT*>(smem + L::r_off);
   float* sv = reinterpret_cast<float*>(smem + L::v_off);
@@ -170,12 +189,13 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
   __shared__ double scratch[2 * 32];
   __shared__ int flag;
 
-  const int lane = threadIdx.x;
-  const int n0 = blockIdx.x * kStripW;
-  const int n = n0 + lane;
+  const int lane = threadIdx.x & 31;
+  const int col0 = (threadIdx.x >> 5) * (kLanes * E);  // this warp's first column in the tile
+  const bool leader = threadIdx.x == 0;
+  const int n0 = blockIdx.x * W;
   const int nchunks = (T + TT - 1) / TT;
 
-  if (lane == 0) {
+  if (leader) {
     tma_prefetch_desc(&tm_r);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_z);
@@ -185,7 +205,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
-  __syncwarp();
+  strip_sync<NW>();
 
   auto issue = [&](int chunk, int s) {
     mbar_expect_tx(&full[s], L::stage_tx);
@@ -193,12 +213,19 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
     tma_load_2d(sv + (size_t)s * L::kTile, &tm_v, n0, chunk * TT, &full[s]);
     tma_load_2d(sz + (size_t)s * L::kTile, &tm_z, n0, chunk * TT, &full[s]);
   };
-  if (lane == 0) {
+  if (leader) {
     for (int i = 0; i < S && i < nchunks; ++i) issue(nchunks - 1 - i, i);
   }
 
-  float v_next = n < N ? __ldg(last_value + n) : 0.f;
-  float a_next = 0.f;
+  float v_next[E], a_next[E];
+  bool live[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int n = n0 + col0 + e * kLanes + lane;
+    live[e] = n < N;
+    v_next[e] = live[e] ? __ldg(last_value + n) : 0.f;
+    a_next[e] = 0.f;
+  }
   double s1 = 0.0, s2 = 0.0;
 
   for (int i = 0; i < nchunks; ++i) {
@@ -206,46 +233,91 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__
     const int s = i % S;
     const int o = i & 1;
     mbar_wait(&full[s], (uint32_t)((i / S) & 1));
-    const RT* r_t = sr + (size_t)s * L::kTile + lane;
-    const float* v_t = sv + (size_t)s * L::kTile + lane;
-    const uint8_t* z_t = sz + (size_t)s * L::kTile + lane;
-    float* a_t = sa + (size_t)o * L::kTile + lane;
-    float* vt_t = svt + (size_t)o * L::kTile + lane;
+    const RT* r_t = sr + (size_t)s * L::kTile + col0 + lane;
+    const float* v_t = sv + (size_t)s * L::kTile + col0 + lane;
+    const uint8_t* z_t = sz + (size_t)s * L::kTile + col0 + lane;
+    float* a_t = sa + (size_t)o * L::kTile + col0 + lane;
+    float* vt_t = svt + (size_t)o * L::kTile + col0 + lane;
     const int t0 = c * TT;
+
+    if (i == 0) {
+      // top chunk: may be partial (rows >= T are TMA zero fill) and holds the last row
+#pragma unroll 1
+      for (int tt = TT - 1; tt >= 0; --tt) {
+        const int t = t0 + tt;
+        if (t >= T) continue;
 #pragma unroll
-    for (int tt = TT - 1; tt >= 0; --tt) {
-      const int t = t0 + tt;
-      if (t < T) {  // warp-uniform; false only in the top chunk
-        const RT r = r_t[tt * kStripW];
-        const float v = v_t[tt * kStripW];
-        const unsigned z = z_t[tt * kStripW];
-        const float a = (t == T - 1) ? gae_last_row<RT>(r, v, z, v_next, gamma)
-                                     : gae_row<RT>(r, v, v_next, a_next, z, gamma, gamma_lambda);
-        a_t[tt * kStripW] = a;
-        vt_t[tt * kStripW] = __fadd_rn(a, v);
-        if (n < N) {
-          s1 += (double)a;
-          s2 += (double)a * (double)a;
+        for (int e = 0; e < E; ++e) {
+          const int at = tt * W + e * kLanes;
+          const RT r = r_t[at];
+          const float v = v_t[at];
+          const unsigned z = z_t[at];
+          const float a = (t == T - 1)
+                              ? gae_last_row<RT>(r, v, z, v_next[e], gamma)
+                              : gae_row<RT>(r, v, v_next[e], a_next[e], z, gamma, gamma_lambda);
+          a_t[at] = a;
+          vt_t[at] = __fadd_rn(a, v);
+          if (kStats && live[e]) {
+            s1 += (double)a;
+            s2 += (double)a * (double)a;
+          }
+          a_next[e] = a;
+          v_next[e] = v;
         }
-        a_next = a;
-        v_next = v;
       }
+    } else {
+      float v[TT][E];
+      double delta[TT][E], k[TT][E];
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[tt][e] = v_t[tt * W + e * kLanes];
+      }
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int at = tt * W + e * kLanes;
+          const unsigned z = z_t[at];
+          const double r = (double)r_t[at];
+          const float vn = tt == TT - 1 ? v_next[e] : v[tt + 1][e];
+          const double cz = z ? 0.0 : gamma;
+          k[tt][e] = z ? 0.0 : gamma_lambda;
+          delta[tt][e] = __dsub_rn(__dadd_rn(r, __dmul_rn(cz, (double)vn)), (double)v[tt][e]);
+        }
+      }
+#pragma unroll
+      for (int tt = TT - 1; tt >= 0; --tt) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int at = tt * W + e * kLanes;
+          const float a =
+              __double2float_rn(__dadd_rn(delta[tt][e], __dmul_rn(k[tt][e], (double)a_next[e])));
+          a_next[e] = a;
+          a_t[at] = a;
+          vt_t[at] = __fadd_rn(a, v[tt][e]);
+          if (kStats && live[e]) {
+            s1 += (double)a;
+            s2 += (double)a * (double)a;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) v_next[e] = v[0][e];
     }
-    __syncwarp();  // every lane is done reading stage s and writing out-buffer o
-    if (lane == 0) {
-      fence_proxy_async_smem();
+    fence_proxy_async_smem();  // own writes to the out tile -> visible to the async proxy
+    strip_sync<NW>();          // every lane is done reading stage s and writing out-buffer o
+    if (leader) {
       tma_store_2d(&tm_a, sa + (size_t)o * L::kTile, n0, t0);
       tma_store_2d(&tm_vt, svt + (size_t)o * L::kTile, n0, t0);
       bulk_commit();
       if (i + S < nchunks) issue(c - S, s);
       bulk_wait_read<1>();  // the store before this one has left smem: buffer o^1 is free
     }
-    __syncwarp();
+    strip_sync<NW>();
   }
-  if (lane == 0) bulk_wait<0>();
-  if (stats != nullptr) {
-    finish_stats(s1, s2, (double)T * (double)N, workspace, stats, scratch, &flag);
-  }
+  if (leader) bulk_wait<0>();
+  if (kStats) finish_stats(s1, s2, (double)T * (double)N, workspace, stats, scratch, &flag);
 }
 
 // ------------------------------------------------------------------ tensor-map encoding
@@ -270,14 +342,14 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [T, N] row-major array viewed as a 2-D tensor {N (inner), T}; box {32, TT}.
+// [T, N] row-major array viewed as a 2-D tensor {N (inner), T}; box {W, TT}.
 bool make_strip_map(CUtensorMap* map, CUtensorMapDataType dt, size_t elem, const void* base,
-                    long long T, long long N, int TT) {
+                    long long T, long long N, int TT, int W) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return false;
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
   cuuint64_t strides[1] = {(cuuint64_t)N * elem};
-  cuuint32_t box[2] = {(cuuint32_t)kStripW, (cuuint32_t)TT};
+  cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)TT};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -287,36 +359,60 @@ bool make_strip_map(CUtensorMap* map, CUtensorMapDataType dt, size_t elem, const
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <typename RT, int TT, int S>
+template <typename RT, int TT, int S, int E, int NW>
 int launch_tma(const void* rewards, const float* values, const uint8_t* resets,
                const float* last_value, long long T, long long N, double gamma, double gl,
                float* adv, float* vt, double* stats, void* workspace, cudaStream_t st) {
-  using L = GaeTmaSmem<RT, TT, S>;
+  using L = GaeTmaSmem<RT, TT, S, E, NW>;
+  constexpr int W = L::kW;
   CUtensorMap tm_r, tm_v, tm_z, tm_a, tm_vt;
   const CUtensorMapDataType rdt = std::is_same<RT, double>::value
                                       ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  bool ok = make_strip_map(&tm_r, rdt, sizeof(RT), rewards, T, N, TT) &&
-            make_strip_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, values, T, N, TT) &&
-            make_strip_map(&tm_z, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, resets, T, N, TT) &&
-            make_strip_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, adv, T, N, TT) &&
-            make_strip_map(&tm_vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vt, T, N, TT);
+  bool ok = make_strip_map(&tm_r, rdt, sizeof(RT), rewards, T, N, TT, W) &&
+            make_strip_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, values, T, N, TT, W) &&
+            make_strip_map(&tm_z, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, resets, T, N, TT, W) &&
+            make_strip_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, adv, T, N, TT, W) &&
+            make_strip_map(&tm_vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vt, T, N, TT, W);
   if (!ok) {
     set_error("cuTensorMapEncodeTiled failed for GAE strips (T=%lld N=%lld)", T, N);
     return DERL_E_CUDA;
   }
-  auto kern = gae_tma_kernel<RT, TT, S>;
-  static bool attr_set = false;  // once per instantiation; keeps graph captures clean
-  if (!attr_set) {
+  const unsigned grid = (unsigned)((N + W - 1) / W);
+  auto go = [&](auto kern) -> int {
     DERL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)L::bytes));
-    attr_set = true;
+    kern<<<grid, kLanes * NW, L::bytes, st>>>(tm_r, tm_v, tm_z, tm_a, tm_vt, last_value, (int)T,
+                                              (int)N, gamma, gl, workspace, stats);
+    DERL_LAUNCH_CHECK("gae_tma_kernel");
+    return DERL_OK;
+  };
+  return stats != nullptr ? go(gae_tma_kernel<RT, TT, S, E, NW, true>)
+                          : go(gae_tma_kernel<RT, TT, S, E, NW, false>);
+}
+
+// Tile configuration, from the sweep in profiles/r01_gae_tile_sweep.txt (B200, L2 flushed,
+// GB/s of algorithmic bytes at T2048 x N65536 | T128 x N65536 | T128 x N4096):
+//   cfg 0  W= 32, 1 warp,  TT16 S4   5487 | 4360 | 624    8 CTAs/SM; best for very few envs
+//   cfg 1  W= 64, 1 warp x 2 chains/lane, TT8 S4   5656 | 4360 | 484
+//   cfg 2  W=128, 4 warps, TT8  S4   5600 | 4636 | 545    4 CTAs/SM: one wave at N = 65536
+//   cfg 5  W=128, 4 warps, TT16 S3   6190 | 4360 | 623    512-B rows per TMA box line
+// Wider strips mean longer contiguous DRAM bursts per box row, which is what lifts the
+// large shapes from 84 % to 94 % of the measured HBM peak.  DERL_GAE_TMA_CFG overrides.
+template <typename RT>
+int launch_tma_auto(const void* rewards, const float* values, const uint8_t* resets,
+                    const float* last_value, long long T, long long N, double gamma, double gl,
+                    float* adv, float* vt, double* stats, void* workspace, cudaStream_t st) {
+#define DERL_GAE_ARGS rewards, values, resets, last_value, T, N, gamma, gl, adv, vt, stats, workspace, st
+  int cfg = N < 128 ? 0 : (T <= 256 && N > 8192 ? 2 : 5);
+  if (const char* env = getenv("DERL_GAE_TMA_CFG")) cfg = atoi(env);
+  switch (cfg) {
+    case 1: return launch_tma<RT, 8, 4, 2, 1>(DERL_GAE_ARGS);
+    case 2: return launch_tma<RT, 8, 4, 1, 4>(DERL_GAE_ARGS);
+    case 5: return launch_tma<RT, 16, 3, 1, 4>(DERL_GAE_ARGS);
+    default: return launch_tma<RT, 16, 4, 1, 1>(DERL_GAE_ARGS);
   }
-  const unsigned grid = (unsigned)((N + kStripW - 1) / kStripW);
-  kern<<<grid, kStripW, L::bytes, st>>>(tm_r, tm_v, tm_z, tm_a, tm_vt, last_value, (int)T,
-                                        (int)N, gamma, gl, workspace, stats);
-  DERL_LAUNCH_CHECK("gae_tma_kernel");
-  return DERL_OK;
+#undef DERL_GAE_ARGS
 }
 
 template <typename RT>
@@ -426,10 +522,10 @@ int derl_b200_gae(const void* rewards, int rewards_f64, const float* values,
   const bool use_tma = variant == DERL_GAE_TMA || (variant == DERL_GAE_AUTO && tma_ok);
   const double gl = gamma * lambda;  // (1*gamma)*lambda, the reference's association (:62)
   if (use_tma) {
-    return rewards_f64 ? launch_tma<double, 16, 4>(rewards, values, resets, last_value, T, N,
-                                                   gamma, gl, adv, vt, stats, workspace, st)
-                       : launch_tma<float, 16, 4>(rewards, values, resets, last_value, T, N,
-                                                  gamma, gl, adv, vt, stats, workspace, st);
+    return rewards_f64 ? launch_tma_auto<double>(rewards, values, resets, last_value, T, N,
+                                                 gamma, gl, adv, vt, stats, workspace, st)
+                       : launch_tma_auto<float>(rewards, values, resets, last_value, T, N,
+                                                gamma, gl, adv, vt, stats, workspace, st);
   }
   return rewards_f64 ? launch_direct<double>(rewards, values, resets, last_value, T, N, gamma, gl,
                                              adv, vt, stats, workspace, st)

@@ -1,0 +1,91 @@
+"""Launches each hand-written kernel a few times at its headline size, for ncu captures:
+
+  python tools/profile_kernels.py                       # plain run (must exit 0 first)
+  ncu --set full --clock-control none --import-source on \
+      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns' -c 16 \
+      -o gpurun_out/kernels python tools/profile_kernels.py
+
+Sizes: gather = one 131072-row minibatch out of a 4096x128 frame-stack rollout (14.8 GB,
+config 3); GAE = T2048 x N65536 (config 5 maximum, 2.28 GB of traffic); loss = B 131072.
+Prints CUDA-event times so the plain run doubles as a quick microbenchmark.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import derl_b200  # noqa: E402,F401
+
+K = torch.ops.derl_b200
+DEV = "cuda"
+REPS = int(os.environ.get("REPS", "3"))
+
+
+def timed(name, fn, nbytes):
+  times = []
+  for _ in range(REPS):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    fn()
+    e.record()
+    torch.cuda.synchronize()
+    times.append(s.elapsed_time(e))
+  ms = min(times)
+  print(f"{name:28s} {ms:9.4f} ms  {nbytes / ms / 1e6:9.1f} GB/s", flush=True)
+
+
+def main():
+  gen = torch.Generator(device=DEV).manual_seed(0)
+  # ---- GAE sweep maximum
+  nsteps, nenvs = 2048, 65536
+  rewards = torch.randn(nsteps, nenvs, device=DEV, generator=gen)
+  values = torch.randn(nsteps, nenvs, device=DEV, generator=gen)
+  resets = torch.rand(nsteps, nenvs, device=DEV, generator=gen) < 0.01
+  last = torch.randn(nenvs, device=DEV, generator=gen)
+  nbytes = 17.0 * nsteps * nenvs
+  timed("gae_tma   T2048 N65536", lambda: K.gae(rewards, values, resets, last, .99, .95, False, 2),
+        nbytes)
+  timed("gae_direct T2048 N65536", lambda: K.gae(rewards, values, resets, last, .99, .95, False, 1),
+        nbytes)
+  nsm = 128 * 4096
+  timed("gae_tma   T128 N4096", lambda: K.gae(rewards[:128, :4096].contiguous(),
+                                               values[:128, :4096].contiguous(),
+                                               resets[:128, :4096].contiguous(), last[:4096],
+                                               .99, .95, False, 2), 17.0 * nsm)
+  del rewards, values, resets
+  # ---- loss, config-3 minibatch
+  nb, nact = 131072, 4
+  logits = torch.randn(nb, nact, device=DEV, generator=gen)
+  vals = torch.randn(nb, 1, device=DEV, generator=gen)
+  acts = torch.randint(0, nact, (nb,), device=DEV, generator=gen)
+  vec = lambda: torch.randn(nb, device=DEV, generator=gen)
+  old_lp, adv, vt, vold = vec() * .1 - 1.4, vec(), vec().reshape(nb, 1), vec().reshape(nb, 1)
+  timed("ppo_loss_categorical B131072",
+        lambda: K.ppo_loss_categorical(logits, vals, acts, old_lp, adv, vt, vold, .1, .25, .01),
+        (8 * nact + 32.0) * nb)
+  loc, scale = torch.randn(nb, 6, device=DEV, generator=gen), torch.rand(nb, 6, device=DEV) + .5
+  cact = torch.randn(nb, 6, device=DEV, generator=gen)
+  timed("ppo_loss_gaussian B131072",
+        lambda: K.ppo_loss_gaussian(loc, scale, vals, cact, old_lp, adv, vt, vold, .2, .25, 0.),
+        (20 * 6 + 24.0) * nb)
+  # ---- gather, config-3 minibatch
+  nsamples = int(os.environ.get("SAMPLES", 4096 * 128))
+  obs = torch.randint(0, 256, (nsamples, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
+  perm = torch.from_numpy(np.random.RandomState(0).permutation(nsamples)).to(DEV)
+  mb = nsamples // 4
+  state = {"i": 0}
+
+  def gather():
+    state["i"] = (state["i"] + 1) % 4
+    return K.gather_rows(obs, perm, state["i"] * mb, mb)
+  timed("gather_rows_tma 131072x28224", gather, (8 + 2 * 28224.0) * mb)
+  cols = [adv.repeat(4), vt.reshape(-1).repeat(4), vold.reshape(-1).repeat(4), old_lp.repeat(4),
+          acts.repeat(4)]
+  timed("gather_columns 5 cols", lambda: K.gather_columns(cols, perm, mb, mb, 0),
+        (8 + 2 * 24.0) * mb)
+
+
+if __name__ == "__main__":
+  main()
