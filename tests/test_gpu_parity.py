@@ -112,6 +112,26 @@ def test_gae_random_vs_oracle_bit_exact(nsteps, nenvs, rdtype, reset_prob):
     np.testing.assert_allclose(stats, [a64.sum(), (a64 * a64).sum(), a64.size], rtol=1e-12)
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 5])
+def test_gae_tma_tile_configurations_are_bit_identical(cfg, monkeypatch):
+  """Every TMA tile shape (strip width, warps per CTA, chains per lane, stages) computes the
+  same bits as the oracle, including ragged strips and a partial top time-chunk."""
+  monkeypatch.setenv("DERL_GAE_TMA_CFG", str(cfg))
+  for nsteps, nenvs, rdtype in ((100, 1040, np.float64), (16, 128, np.float32),
+                                (3, 48, np.float32), (257, 4096, np.float32)):
+    rng = np.random.RandomState(cfg * 100 + nsteps)
+    rewards = rng.standard_normal((nsteps, nenvs)).astype(rdtype)
+    values = rng.standard_normal((nsteps, nenvs)).astype(np.float32)
+    resets = rng.random((nsteps, nenvs)) < 0.05
+    last_value = rng.standard_normal(nenvs).astype(np.float32)
+    want_a, want_vt = O.gae_c(rewards, values, resets, last_value, 0.99, 0.95)
+    adv, vt, stats = run_gae(rewards, values, resets, last_value, 0.99, 0.95, 2, True)
+    np.testing.assert_array_equal(adv, want_a)
+    np.testing.assert_array_equal(vt, want_vt)
+    a64 = want_a.astype(np.float64)
+    np.testing.assert_allclose(stats, [a64.sum(), (a64 * a64).sum(), a64.size], rtol=1e-12)
+
+
 def test_gae_special_values_follow_ieee_like_numpy():
   """inf / nan / signed zeros propagate exactly as NumPy's float64 arithmetic does."""
   nsteps, nenvs = 6, 32
@@ -513,6 +533,37 @@ def test_full_ppo_update_matches_reference_losses(golden, name, kind):
   # a sum over 1.7 M parameters with cancellation: 1e-4 of the sum is ~1e-8 per parameter
   np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-4)
   torch.backends.cudnn.allow_tf32 = True
+
+
+def test_space_to_depth_first_conv_equals_plain_formulation():
+  """NatureCNNBase runs the 8x8/4 stem as a 2x2/1 conv on the space-to-depth tensor with
+  re-indexed weights (derl_b200/models.py): same parameters, same function as the
+  reference's NCHW float/255 pipeline (derl/models.py:117-124) — outputs and parameter
+  gradients agree to float32 rounding (TF32 off)."""
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.manual_seed(0)
+  model = d.NatureCNNModel([6, 1])
+  frames = torch.randint(0, 256, (37, 84, 84, 4), dtype=torch.uint8, device=DEV)
+  outs = {}
+  for s2d in (True, False):
+    d.NatureCNNBase.space_to_depth = s2d
+    model.zero_grad()
+    logits, values = model(frames)
+    (logits.square().sum() + values.sum()).backward()
+    outs[s2d] = (logits.detach().clone(), values.detach().clone(),
+                 [p.grad.clone() for p in model.parameters()])
+  d.NatureCNNBase.space_to_depth = True
+  torch.backends.cudnn.allow_tf32 = True
+  for a, b in zip(outs[True][:2], outs[False][:2]):
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+  for a, b in zip(outs[True][2], outs[False][2]):
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+  # and the CPU path (reference formulation) agrees with the GPU one
+  cpu = d.NatureCNNModel([6, 1]).to("cpu")
+  cpu.load_state_dict(model.state_dict())
+  want = cpu(frames.cpu())[0]
+  assert torch.allclose(outs[True][0].cpu(), want, rtol=1e-4, atol=1e-5)
 
 
 # =============================================================================== plumbing
