@@ -79,7 +79,9 @@ class GradientAllReduce:
     self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
     offset = 0
     for p in params:
-      p.grad = self.flat[offset:offset + p.numel()].view_as(p)
+      # same strides as the parameter (channels_last conv weights stay channels_last): autograd's
+      # gradient-layout contract and the fused optimizers require grad.layout == param.layout
+      p.grad = torch.as_strided(self.flat, p.size(), p.stride(), storage_offset=offset)
       offset += p.numel()
     self.params = params
 

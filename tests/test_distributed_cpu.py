@@ -75,6 +75,24 @@ def test_env_shard_and_rollout_slicing():
   np.testing.assert_array_equal(part["state"]["latest_observations"], [2, 3])
 
 
+def test_flat_gradient_views_keep_the_parameter_layout():
+  """channels_last conv weights get channels_last gradient views into the flat buffer."""
+  model = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.Flatten(), torch.nn.Linear(8, 2))
+  model.to(memory_format=torch.channels_last)
+  sync = parallel.GradientAllReduce(model)
+  for p in model.parameters():
+    assert p.grad.stride() == p.stride() and p.grad.shape == p.shape
+  model(torch.randn(5, 4, 3, 3)).sum().backward()
+  want = [p.grad.clone() for p in model.parameters()]
+  opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+  opt.zero_grad(set_to_none=False)
+  assert float(sync.flat.abs().sum()) == 0.0
+  model(torch.randn(5, 4, 3, 3)).sum().backward()
+  opt.step()
+  assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())
+  assert sum(w.numel() for w in want) == sync.flat.numel()
+
+
 def test_single_process_is_a_noop():
   for key in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
     os.environ.pop(key, None)
