@@ -40,6 +40,7 @@ SIGNATURES = {
     "derl_b200_ppo_loss_gaussian": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr,
                                            _ptr, _int, _f64, _f64, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr, _ptr, _size, _ptr]),
+    "derl_b200_frames_to_s2d": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _f64, _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,
                                   _f64, _ptr, _ptr, _ptr]),
 }

@@ -1,0 +1,109 @@
+// K4 — frame-stack preparation for the network stem: uint8 NHWC frames -> space-to-depth,
+// scaled floating-point, channels-last tensor in ONE pass.
+//
+// Replaces the reference's NatureCNNBase.forward input pipeline (derl/models.py:117-123:
+// permute NHWC->NCHW, `.float() / 255`, `.contiguous()` transpose copy) for the stem evaluated
+// as a 2x2/stride-1 convolution over the space-to-depth(s) tensor (derl_b200/models.py):
+//     dst[b, Y, X, (i*s + j)*C + c] = float(src[b, s*Y + i, s*X + j, c]) / divisor
+// With s*C == 16 (Atari: s = 4, C = 4) a (j, c) run is 16 contiguous bytes on both sides:
+// one thread moves one run — a perfectly coalesced 16-B read stream and 64-B (fp32) or 32-B
+// (bf16/fp16) full-sector writes.  HBM-bound: 1 B read + sizeof(out) B written per element.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace derl {
+namespace {
+
+template <typename OT>
+__device__ __forceinline__ OT to_out(float x);
+template <>
+__device__ __forceinline__ float to_out<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float x) {
+  return __float2bfloat16_rn(x);
+}
+template <>
+__device__ __forceinline__ __half to_out<__half>(float x) { return __float2half_rn(x); }
+
+// granule g (source order) = (b, y = s*Y + i, X): 16 source bytes at g*16
+template <typename OT>
+__global__ void __launch_bounds__(256)
+frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, long long granules,
+                     int height, int wx, int s, float divisor) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < granules;
+       g += stride) {
+    const uint4 raw = __ldg(src + g);
+    const long long by = g / wx;                  // b*height + y
+    const int X = (int)(g - by * wx);
+    const long long b = by / height;
+    const int y = (int)(by - b * height);
+    const int Y = y / s, i = y - Y * s;
+    const long long out = ((((b * (height / s) + Y) * wx + X) * s) + i) * 16;
+    const unsigned words[4] = {raw.x, raw.y, raw.z, raw.w};
+    alignas(16) OT vals[16];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float f = (float)((words[w] >> (8 * k)) & 0xffu);
+        vals[w * 4 + k] = to_out<OT>(divisor == 1.f ? f : __fdiv_rn(f, divisor));
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + out);
+    const uint4* v = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(OT) * 16 / 16); ++q) o[q] = v[q];
+  }
+}
+
+template <typename OT>
+int launch(const void* src, void* dst, long long granules, int height, int wx, int s,
+           float divisor, cudaStream_t st) {
+  long long blocks = (granules + 255) / 256;
+  const long long cap = (long long)sm_count() * 64;
+  if (blocks > cap) blocks = cap;
+  frames_to_s2d_kernel<OT><<<(unsigned)blocks, 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<OT*>(dst), granules, height, wx, s,
+      divisor);
+  DERL_LAUNCH_CHECK("frames_to_s2d_kernel");
+  return DERL_OK;
+}
+
+}  // namespace
+}  // namespace derl
+
+using namespace derl;
+
+extern "C" int derl_b200_frames_to_s2d(const uint8_t* src, int64_t batch, int64_t height,
+                                       int64_t width, int64_t channels, int64_t block,
+                                       void* dst, int dst_dtype, double divisor, void* stream) {
+  DERL_REQUIRE(src && dst && batch >= 0, "frames_to_s2d: bad arguments");
+  DERL_REQUIRE(block >= 1 && block * channels == 16,
+               "frames_to_s2d: needs block*channels == 16 (got block=%lld channels=%lld)",
+               (long long)block, (long long)channels);
+  DERL_REQUIRE(height >= block && width >= block && height % block == 0 && width % block == 0,
+               "frames_to_s2d: height=%lld and width=%lld must be multiples of block=%lld",
+               (long long)height, (long long)width, (long long)block);
+  DERL_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
+               "frames_to_s2d: src and dst must be 16-byte aligned");
+  DERL_REQUIRE(dst_dtype >= 0 && dst_dtype <= 2, "frames_to_s2d: dst_dtype %d not in {0,1,2}",
+               dst_dtype);
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  if (batch == 0) return DERL_OK;
+  const int wx = (int)(width / block);
+  const long long granules = batch * height * wx;
+  cudaStream_t st = as_stream(stream);
+  switch (dst_dtype) {
+    case DERL_DTYPE_BF16:
+      return launch<__nv_bfloat16>(src, dst, granules, (int)height, wx, (int)block,
+                                   (float)divisor, st);
+    case DERL_DTYPE_F16:
+      return launch<__half>(src, dst, granules, (int)height, wx, (int)block, (float)divisor, st);
+    default:
+      return launch<float>(src, dst, granules, (int)height, wx, (int)block, (float)divisor, st);
+  }
+}

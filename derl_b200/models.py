@@ -89,26 +89,27 @@ class NatureCNNBase(nn.Sequential):
     space-to-depth(s) tensor with s*s*C channels and re-indexed weights (same parameters,
     same sums).  For the Atari stem (8x8 / 4 over 4 channels) this turns a C=4 convolution,
     for which cuDNN only has a scalar NHWC engine (13 ms per 16384 frames on B200, 49 % of
-    the whole update), into a C=64 one that runs on tensor cores; the /255 is folded into
-    the re-indexed weights so the fp32 copy of the frames is written once and never rescaled.
+    the whole update), into a C=64 one that runs on tensor cores.  On the GPU the
+    re-indexing, the uint8 -> float cast and the /255 are one pass of the frames_to_s2d
+    kernel (IEEE division: the same input values as the reference's `.float() / 255`).
     """
     conv = self[0]
     batch, height, width, chans = frames.shape
     s = conv.stride[0]
-    if s * chans == 16:
-      # (j, c) runs of s*chans = 16 bytes are contiguous on both sides: move them as one
-      # 16-byte element each (complex128 is only a 128-bit container here, bits untouched)
-      wide = frames.view(batch, height, width * chans).view(torch.complex128)
-      s2d = wide.view(batch, height // s, s, width // s).permute(0, 1, 3, 2).contiguous()
-      s2d = s2d.view(torch.uint8)
+    if frames.is_cuda and s * chans == 16:
+      from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
+      dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") \
+          else conv.weight.dtype
+      s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0)
     else:
       blocks = frames.view(batch, height // s, s, width // s, s, chans)
-      s2d = blocks.permute(0, 1, 3, 2, 4, 5).contiguous()
-    s2d = s2d.view(batch, height // s, width // s, s * s * chans).permute(0, 3, 1, 2)
+      s2d = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s, -1)
+      s2d = s2d.float() / 255
+    s2d = s2d.permute(0, 3, 1, 2)   # NHWC storage seen as NCHW == channels_last
     weight = conv.weight.view(conv.out_channels, chans, 2, s, 2, s).permute(0, 3, 5, 1, 2, 4)
-    weight = (weight.reshape(conv.out_channels, s * s * chans, 2, 2) * (1.0 / 255)).contiguous(
+    weight = weight.reshape(conv.out_channels, s * s * chans, 2, 2).contiguous(
         memory_format=torch.channels_last)
-    hidden = nn.functional.conv2d(s2d.float(), weight, conv.bias)
+    hidden = nn.functional.conv2d(s2d, weight, conv.bias)
     for layer in list(self.children())[1:]:
       hidden = layer(hidden)
     return hidden

@@ -218,6 +218,37 @@ def _(columns, perm, start, count, moments_col=-1):
   return outs + [columns[0].new_empty(3 if moments_col >= 0 else 0, dtype=torch.float64)]
 
 
+# --------------------------------------------------------------------------- K4: frames
+_S2D_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+@torch.library.custom_op("derl_b200::frames_to_s2d", mutates_args=(), device_types="cuda")
+def frames_to_s2d(frames: Tensor, block: int, dtype: torch.dtype, divisor: float) -> Tensor:
+  """uint8 NHWC frames [B,H,W,C] -> [B, H/block, W/block, block*block*C] of `dtype`, values
+  divided by `divisor` in float32 (space-to-depth + cast + scale in one pass)."""
+  _dense(frames, "frames", (torch.uint8,))
+  _need(frames.dim() == 4, f"frames must be [B, H, W, C], got {tuple(frames.shape)}")
+  _need(dtype in _S2D_DTYPES, f"dtype must be one of {list(_S2D_DTYPES)}")
+  batch, height, width, chans = frames.shape
+  _need(block * chans == 16 and height % block == 0 and width % block == 0,
+        f"frames_to_s2d needs block*C == 16 and H, W multiples of block (got {tuple(frames.shape)}, "
+        f"block={block})")
+  out = torch.empty((batch, height // block, width // block, block * block * chans), dtype=dtype,
+                    device=frames.device)
+  with _device_of(frames, "frames_to_s2d"):
+    _lib.check(_lib.load().derl_b200_frames_to_s2d(_p(frames), batch, height, width, chans, block,
+                                                   _p(out), _S2D_DTYPES[dtype], float(divisor),
+                                                   _stream(frames)), "frames_to_s2d")
+  return out
+
+
+@frames_to_s2d.register_fake
+def _(frames, block, dtype, divisor):
+  batch, height, width, chans = frames.shape
+  return frames.new_empty((batch, height // block, width // block, block * block * chans),
+                          dtype=dtype)
+
+
 # --------------------------------------------------------------------------- K3: PPO loss
 def _loss_common(head, values, old_log_prob, advantages, value_targets, old_values):
   ref = head if head is not None else values

@@ -174,6 +174,20 @@ int derl_b200_ppo_loss_gaussian(const float* loc_dev, const float* scale_dev, in
                                 float* dscale_dev, float* dvalues_dev, float* stats_dev,
                                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ K4: frame preparation
+ * Replaces the input pipeline of NatureCNNBase.forward (derl/models.py:117-123: NHWC->NCHW
+ * permute, `.float() / 255`, `.contiguous()`) with one pass that also applies the
+ * space-to-depth re-indexing under which the 8x8/stride-4 stem is a 2x2/stride-1 convolution:
+ *     dst[b, Y, X, (i*block + j)*C + c] = dtype(float(src[b, block*Y + i, block*X + j, c]) / divisor)
+ * src: uint8 [batch, height, width, channels] (NHWC), block*channels == 16, height and width
+ * multiples of block; dst: [batch, height/block, width/block, block*block*channels] of
+ * dst_dtype.  The division is IEEE float32 (bit-identical to `.float() / 255`); divisor 1 skips it.
+ */
+enum { DERL_DTYPE_F32 = 0, DERL_DTYPE_BF16 = 1, DERL_DTYPE_F16 = 2 };
+int derl_b200_frames_to_s2d(const uint8_t* src_dev, int64_t batch, int64_t height,
+                            int64_t width, int64_t channels, int64_t block, void* dst_dev,
+                            int dst_dtype, double divisor, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations on HOST arrays (what a NumPy caller such as the reference's
  * TransformInteractions hook holds): the library allocates device scratch, copies in on

@@ -535,6 +535,26 @@ def test_full_ppo_update_matches_reference_losses(golden, name, kind):
   torch.backends.cudnn.allow_tf32 = True
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_frames_to_s2d_kernel_bit_exact(dtype):
+  """K4: uint8 NHWC -> space-to-depth, /255 (IEEE float32 division), cast — against the same
+  expression evaluated by NumPy / torch on the host, bit for bit."""
+  rng = np.random.RandomState(4)
+  for batch, height, width in ((3, 84, 84), (1, 4, 4), (257, 8, 12)):
+    frames = rng.randint(0, 256, (batch, height, width, 4)).astype(np.uint8)
+    out = K.frames_to_s2d(cuda(frames), 4, dtype, 255.0)
+    blocks = frames.reshape(batch, height // 4, 4, width // 4, 4, 4).transpose(0, 1, 3, 2, 4, 5)
+    want = torch.from_numpy(blocks.reshape(batch, height // 4, width // 4, 64).astype(np.float32)
+                            / np.float32(255)).to(dtype)
+    assert out.shape == want.shape and out.dtype == dtype
+    assert torch.equal(out.cpu(), want)
+  raw = K.frames_to_s2d(cuda(frames), 4, torch.float32, 1.0)
+  assert torch.equal(raw.cpu(), torch.from_numpy(
+      blocks.reshape(batch, height // 4, width // 4, 64).astype(np.float32)))
+  with pytest.raises(ValueError, match="block\\*C == 16"):
+    K.frames_to_s2d(cuda(frames), 2, torch.float32, 255.0)
+
+
 def test_space_to_depth_first_conv_equals_plain_formulation():
   """NatureCNNBase runs the 8x8/4 stem as a 2x2/1 conv on the space-to-depth tensor with
   re-indexed weights (derl_b200/models.py): same parameters, same function as the
