@@ -58,6 +58,8 @@ def parse_args():
   p.add_argument("--cpu-envs", type=int, default=32,
                  help="envs of the bounded CPU-baseline sample (same horizon/epochs/minibatches)")
   p.add_argument("--no-e2e", action="store_true")
+  p.add_argument("--no-alt", action="store_true",
+                 help="skip the informational bf16-autocast-network measurement")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--gae-sweep", action="store_true", help="also time the GAE kernel sweep")
   return p.parse_args()
@@ -382,6 +384,7 @@ def run_ours(args, rank, world, local):
                 "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
                 "launch_ms": ms, "launches_timed": n}
   per_elem = {"gae": 17.0 * horizon * nenvs + 4 * nenvs,
+              "frames_to_s2d": 5.0 * OBS_ROW_BYTES * min(args.micro_batch, mb_rows),
               "ppo_loss_categorical": (8 * args.nactions + 32) * min(args.micro_batch, mb_rows),
               "gather_columns": (8 + 2 * (8 + 4 + 4 + 4 + 4 + 4 + 1)) * mb_rows,
               "normalize": 8.0 * mb_rows}
@@ -391,6 +394,16 @@ def run_ours(args, rank, world, local):
       entry["GBps"] = per_elem[name] / ms / 1e6
       entry["frac"] = entry["GBps"] / hbm_peak
     kernels[name] = entry
+
+  # ---- informational: the same update with the network under bf16 autocast
+  alt = None
+  if args.net != "bf16" and not args.no_alt:
+    model.autocast_dtype = torch.bfloat16
+    sec_a, _ = timed_updates(alg, runner, nbatches, max(1, args.steps - 1), 2, world, False)
+    model.autocast_dtype = None
+    alt = {"network": "bf16 autocast (parameters fp32)",
+           "value": samples_per_step * max(1, args.steps - 1) / sec_a, "unit": "samples/s",
+           "ms_per_step": sec_a / max(1, args.steps - 1) * 1e3}
 
   # ---- e2e: rollout in pinned host memory, uploaded inside the timed region
   e2e = None
@@ -432,7 +445,7 @@ def run_ours(args, rank, world, local):
                   "bf16": "f32 params, bf16 autocast network; GAE f64 registers; u8 gather"}[args.net],
         "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_network": alt,
         "last_loss": last_loss,
     }
     if sweep is not None:

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256)
 frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, long long granules,
                      int height, int wx, int s, float divisor) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const float recip = __frcp_rn(divisor);
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < granules;
        g += stride) {
     const uint4 raw = __ldg(src + g);
@@ -48,8 +49,16 @@ frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, long l
     for (int w = 0; w < 4; ++w) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float f = (float)((words[w] >> (8 * k)) & 0xffu);
-        vals[w * 4 + k] = to_out<OT>(divisor == 1.f ? f : __fdiv_rn(f, divisor));
+        // byte -> float without the conversion pipe: 0x4B0000bb is 2^23 + bb exactly
+        const float f = __uint_as_float(__byte_perm(words[w], 0x4B000000u, 0x7440 + k)) - 8388608.f;
+        float q = f;
+        if (divisor != 1.f) {
+          // correctly rounded f / divisor for the 256 byte values: reciprocal estimate plus one
+          // FMA residual step (verified bit-exact against IEEE division in the tests)
+          q = __fmul_rn(f, recip);
+          q = __fmaf_rn(__fmaf_rn(-q, divisor, f), recip, q);
+        }
+        vals[w * 4 + k] = to_out<OT>(q);
       }
     }
     uint4* o = reinterpret_cast<uint4*>(dst + out);

@@ -60,6 +60,30 @@ def _broadcast(ndims, forward, module, inputs):
   return strip(outputs)
 
 
+class _ConvBiasReLU(torch.autograd.Function):
+  """conv2d + bias + ReLU as ONE cuDNN call forward (`cudnn_convolution_relu`: the bias add
+  and the activation run in the convolution's epilogue instead of two more passes over the
+  activation tensor), and threshold + `convolution_backward` backward.  The ReLU mask is
+  recovered from the output, so the pre-activation tensor is never materialised or saved."""
+
+  @staticmethod
+  def forward(ctx, inputs, weight, bias, stride, padding):
+    out = torch.cudnn_convolution_relu(inputs, weight, bias, stride, padding, (1, 1), 1)
+    ctx.save_for_backward(inputs, weight, out)
+    ctx.conf = (stride, padding)
+    return out
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    inputs, weight, out = ctx.saved_tensors
+    stride, padding = ctx.conf
+    grad_pre = torch.ops.aten.threshold_backward(grad_out, out, 0)
+    grad_in, grad_w, grad_b = torch.ops.aten.convolution_backward(
+        grad_pre, inputs, weight, [weight.shape[0]], stride, padding, (1, 1), False, (0, 0), 1,
+        [ctx.needs_input_grad[0], True, True])
+    return grad_in, grad_w, grad_b, None, None
+
+
 def _conv_out(size, conv):
   return (size + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) \
       // conv.stride[0] + 1
@@ -82,7 +106,21 @@ class NatureCNNBase(nn.Sequential):
     self.add_module("flatten", nn.Flatten())
     self.add_module("linear", nn.Linear(height * width * convs[-1].out_channels, 512))
 
-  space_to_depth = True  # class-wide switch (tests compare both formulations)
+  space_to_depth = True   # class-wide switches (tests compare the formulations)
+  fused_conv_relu = True
+
+  def _conv_relu(self, hidden, conv, weight=None):
+    """conv + bias + ReLU; one fused cuDNN call on the GPU when the layer allows it."""
+    weight = conv.weight if weight is None else weight
+    bias, stride = conv.bias, conv.stride
+    if weight.shape[2:] != conv.kernel_size:   # re-indexed stem: 2x2 / stride 1
+      stride = (1, 1)
+    if (self.fused_conv_relu and hidden.is_cuda and bias is not None and conv.groups == 1
+        and conv.dilation == (1, 1) and isinstance(conv.padding, tuple)):
+      if hidden.dtype != weight.dtype:         # autocast: run the whole layer in that dtype
+        weight, bias = weight.to(hidden.dtype), bias.to(hidden.dtype)
+      return _ConvBiasReLU.apply(hidden, weight, bias, stride, conv.padding)
+    return torch.relu(nn.functional.conv2d(hidden, weight, bias, stride, conv.padding))
 
   def _first_conv_as_space_to_depth(self, frames):
     """conv(k = 2s, stride s) on NHWC uint8 frames == conv(k = 2, stride 1) on the
@@ -109,8 +147,12 @@ class NatureCNNBase(nn.Sequential):
     weight = conv.weight.view(conv.out_channels, chans, 2, s, 2, s).permute(0, 3, 5, 1, 2, 4)
     weight = weight.reshape(conv.out_channels, s * s * chans, 2, 2).contiguous(
         memory_format=torch.channels_last)
-    hidden = nn.functional.conv2d(s2d, weight, conv.bias)
-    for layer in list(self.children())[1:]:
+    hidden = self._conv_relu(s2d, conv, weight)
+    layers = list(self.children())[2:]          # after conv-0, relu-0
+    while len(layers) >= 2 and isinstance(layers[0], nn.Conv2d) and isinstance(layers[1], nn.ReLU):
+      hidden = self._conv_relu(hidden, layers[0])
+      layers = layers[2:]
+    for layer in layers:                        # flatten, linear
       hidden = layer(hidden)
     return hidden
 

@@ -566,19 +566,22 @@ def test_space_to_depth_first_conv_equals_plain_formulation():
   model = d.NatureCNNModel([6, 1])
   frames = torch.randint(0, 256, (37, 84, 84, 4), dtype=torch.uint8, device=DEV)
   outs = {}
-  for s2d in (True, False):
-    d.NatureCNNBase.space_to_depth = s2d
+  for s2d, fused in ((True, True), (True, False), (False, False)):
+    d.NatureCNNBase.space_to_depth, d.NatureCNNBase.fused_conv_relu = s2d, fused
     model.zero_grad()
     logits, values = model(frames)
     (logits.square().sum() + values.sum()).backward()
-    outs[s2d] = (logits.detach().clone(), values.detach().clone(),
-                 [p.grad.clone() for p in model.parameters()])
-  d.NatureCNNBase.space_to_depth = True
+    outs[s2d, fused] = (logits.detach().clone(), values.detach().clone(),
+                        [p.grad.clone() for p in model.parameters()])
+  d.NatureCNNBase.space_to_depth = d.NatureCNNBase.fused_conv_relu = True
   torch.backends.cudnn.allow_tf32 = True
-  for a, b in zip(outs[True][:2], outs[False][:2]):
-    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
-  for a, b in zip(outs[True][2], outs[False][2]):
-    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+  plain = outs[False, False]
+  for key in ((True, True), (True, False)):
+    for a, b in zip(outs[key][:2], plain[:2]):
+      assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), key
+    for a, b in zip(outs[key][2], plain[2]):
+      assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max())), key
+  outs = {True: outs[True, True]}
   # and the CPU path (reference formulation) agrees with the GPU one
   cpu = d.NatureCNNModel([6, 1]).to("cpu")
   cpu.load_state_dict(model.state_dict())
