@@ -6,8 +6,7 @@
 // as a 2x2/stride-1 convolution over the space-to-depth(s) tensor (derl_b200/models.py):
 //     dst[b, Y, X, (i*s + j)*C + c] = float(src[b, s*Y + i, s*X + j, c]) / divisor
 // With s*C == 16 (Atari: s = 4, C = 4) a (j, c) run is 16 contiguous bytes on both sides:
-// one thread moves one run — a perfectly coalesced 16-B read stream and 64-B (fp32) or 32-B
-// (bf16/fp16) full-sector writes.  HBM-bound: 1 B read + sizeof(out) B written per element.
+// one thread moves one run — fully coalesced writes, 128-B coalesced read segments.  HBM-bound: 1 B read + sizeof(out) B written per element.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -27,22 +26,21 @@ __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float x) {
 template <>
 __device__ __forceinline__ __half to_out<__half>(float x) { return __float2half_rn(x); }
 
-// granule g (source order) = (b, y = s*Y + i, X): 16 source bytes at g*16
-template <typename OT>
+// One thread per 16-byte (j, c) run, enumerated in DESTINATION order t = ((b*HY + Y)*WX + X)*s + i:
+// a warp writes 32 consecutive runs (2 KiB fp32, fully coalesced) and reads s row segments of
+// 32/s consecutive runs each.  Index arithmetic is one 32-bit division per thread.
+template <typename OT, typename IT>
 __global__ void __launch_bounds__(256)
-frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, long long granules,
-                     int height, int wx, int s, float divisor) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
+frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, IT granules, IT wx,
+                     int log2s, float divisor) {
+  const IT stride = (IT)gridDim.x * blockDim.x;
   const float recip = __frcp_rn(divisor);
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < granules;
-       g += stride) {
-    const uint4 raw = __ldg(src + g);
-    const long long by = g / wx;                  // b*height + y
-    const int X = (int)(g - by * wx);
-    const long long b = by / height;
-    const int y = (int)(by - b * height);
-    const int Y = y / s, i = y - Y * s;
-    const long long out = ((((b * (height / s) + Y) * wx + X) * s) + i) * 16;
+  const IT smask = ((IT)1 << log2s) - 1;
+  for (IT t = (IT)blockIdx.x * blockDim.x + threadIdx.x; t < granules; t += stride) {
+    const IT i = t & smask, q = t >> log2s;
+    const IT r = q / wx;             // b*HY + Y
+    const IT X = q - r * wx;
+    const uint4 raw = __ldg(src + (((r << log2s) + i) * wx + X));
     const unsigned words[4] = {raw.x, raw.y, raw.z, raw.w};
     alignas(16) OT vals[16];
 #pragma unroll
@@ -51,32 +49,40 @@ frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, long l
       for (int k = 0; k < 4; ++k) {
         // byte -> float without the conversion pipe: 0x4B0000bb is 2^23 + bb exactly
         const float f = __uint_as_float(__byte_perm(words[w], 0x4B000000u, 0x7440 + k)) - 8388608.f;
-        float q = f;
+        float v = f;
         if (divisor != 1.f) {
           // correctly rounded f / divisor for the 256 byte values: reciprocal estimate plus one
           // FMA residual step (verified bit-exact against IEEE division in the tests)
-          q = __fmul_rn(f, recip);
-          q = __fmaf_rn(__fmaf_rn(-q, divisor, f), recip, q);
+          v = __fmul_rn(f, recip);
+          v = __fmaf_rn(__fmaf_rn(-v, divisor, f), recip, v);
         }
-        vals[w * 4 + k] = to_out<OT>(q);
+        vals[w * 4 + k] = to_out<OT>(v);
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + out);
-    const uint4* v = reinterpret_cast<const uint4*>(vals);
+    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)t * 16);
+    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
 #pragma unroll
-    for (int q = 0; q < (int)(sizeof(OT) * 16 / 16); ++q) o[q] = v[q];
+    for (int c = 0; c < (int)(sizeof(OT) * 16 / 16); ++c) o[c] = v4[c];
   }
 }
 
 template <typename OT>
-int launch(const void* src, void* dst, long long granules, int height, int wx, int s,
-           float divisor, cudaStream_t st) {
+int launch(const void* src, void* dst, long long granules, int wx, int s, float divisor,
+           cudaStream_t st) {
   long long blocks = (granules + 255) / 256;
   const long long cap = (long long)sm_count() * 64;
   if (blocks > cap) blocks = cap;
-  frames_to_s2d_kernel<OT><<<(unsigned)blocks, 256, 0, st>>>(
-      reinterpret_cast<const uint4*>(src), reinterpret_cast<OT*>(dst), granules, height, wx, s,
-      divisor);
+  int log2s = 0;
+  while ((1 << log2s) < s) ++log2s;
+  const uint4* in = reinterpret_cast<const uint4*>(src);
+  OT* out = reinterpret_cast<OT*>(dst);
+  if (granules < (1ll << 31)) {
+    frames_to_s2d_kernel<OT, unsigned><<<(unsigned)blocks, 256, 0, st>>>(
+        in, out, (unsigned)granules, (unsigned)wx, log2s, divisor);
+  } else {
+    frames_to_s2d_kernel<OT, unsigned long long><<<(unsigned)blocks, 256, 0, st>>>(
+        in, out, (unsigned long long)granules, (unsigned long long)wx, log2s, divisor);
+  }
   DERL_LAUNCH_CHECK("frames_to_s2d_kernel");
   return DERL_OK;
 }
@@ -108,11 +114,10 @@ extern "C" int derl_b200_frames_to_s2d(const uint8_t* src, int64_t batch, int64_
   cudaStream_t st = as_stream(stream);
   switch (dst_dtype) {
     case DERL_DTYPE_BF16:
-      return launch<__nv_bfloat16>(src, dst, granules, (int)height, wx, (int)block,
-                                   (float)divisor, st);
+      return launch<__nv_bfloat16>(src, dst, granules, wx, (int)block, (float)divisor, st);
     case DERL_DTYPE_F16:
-      return launch<__half>(src, dst, granules, (int)height, wx, (int)block, (float)divisor, st);
+      return launch<__half>(src, dst, granules, wx, (int)block, (float)divisor, st);
     default:
-      return launch<float>(src, dst, granules, (int)height, wx, (int)block, (float)divisor, st);
+      return launch<float>(src, dst, granules, wx, (int)block, (float)divisor, st);
   }
 }

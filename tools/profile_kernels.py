@@ -81,6 +81,10 @@ def main():
     state["i"] = (state["i"] + 1) % 4
     return K.gather_rows(obs, perm, state["i"] * mb, mb)
   timed("gather_rows_tma 131072x28224", gather, (8 + 2 * 28224.0) * mb)
+  frames = obs[:16384]
+  for dt, nb in ((torch.float32, 5.0), (torch.bfloat16, 3.0)):
+    timed(f"frames_to_s2d 16384 {str(dt)[6:]}", lambda: K.frames_to_s2d(frames, 4, dt, 255.0),
+          nb * frames.numel())
   cols = [adv.repeat(4), vt.reshape(-1).repeat(4), vold.reshape(-1).repeat(4), old_lp.repeat(4),
           acts.repeat(4)]
   timed("gather_columns 5 cols", lambda: K.gather_columns(cols, perm, mb, mb, 0),
