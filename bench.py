@@ -52,7 +52,7 @@ def parse_args():
   p.add_argument("--epochs", type=int, default=4)
   p.add_argument("--minibatches", type=int, default=4)
   p.add_argument("--nactions", type=int, default=4)
-  p.add_argument("--micro-batch", type=int, default=16384)
+  p.add_argument("--micro-batch", type=int, default=32768)
   p.add_argument("--net", choices=("tf32", "fp32", "bf16"), default="tf32",
                  help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
   p.add_argument("--cpu-envs", type=int, default=32,
