@@ -1,2 +1,3 @@
 from .common import Loss, Trainer, Alg, r_squared, total_norm
+from .graphed import GraphedTrainer
 from .ppo import PPOLoss, PPO

@@ -589,6 +589,42 @@ def test_space_to_depth_first_conv_equals_plain_formulation():
   assert torch.allclose(outs[True][0].cpu(), want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("kind", ["mujoco", "atari"])
+def test_graphed_trainer_matches_eager_trainer(kind):
+  """GraphedTrainer (CUDA-graph replay of forward + fused loss + backward + clip + Adam) walks
+  the same parameter trajectory as the eager Trainer on the same minibatch stream."""
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  results = {}
+  for graphed in (False, True):
+    torch.manual_seed(0)
+    model = d.MuJoCoModel(17, [6, 1]) if kind == "mujoco" else d.NatureCNNModel([4, 1])
+    policy = d.ActorCriticPolicy(model)
+    nenvs, horizon = (None, 256) if kind == "mujoco" else (4, 32)
+    source = d.SyntheticRolloutRunner(policy, kind, nenvs, horizon, nsteps=None, device=DEV, seed=2)
+    runner = d.ppo_runner_wrap(source, num_epochs=2, num_minibatches=4)
+    if graphed:
+      lr = d.LinearAnneal(1e-3, 10 ** 6, device=DEV)
+      opt = torch.optim.Adam(model.parameters(), lr=lr.get_tensor(), eps=1e-5, capturable=True)
+      trainer = d.GraphedTrainer(opt, anneals=[lr], max_grad_norm=.5, warmup=2)
+    else:
+      lr = d.LinearAnneal(1e-3, 10 ** 6)
+      opt = torch.optim.Adam(model.parameters(), lr=lr.get_tensor(), eps=1e-5)
+      trainer = d.Trainer(opt, anneals=[lr], max_grad_norm=.5)
+    alg = d.PPO(runner, trainer, cliprange=.2)
+    np.random.seed(4)
+    it = runner.run()
+    losses = [alg.step(next(it)).item() for _ in range(20)]
+    results[graphed] = (losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]),
+                        alg.loss_fn.call_count, trainer.step_count)
+    if graphed:
+      assert trainer.replays == 18
+  torch.backends.cudnn.allow_tf32 = True
+  np.testing.assert_allclose(results[True][0], results[False][0], rtol=1e-4, atol=1e-6)
+  assert torch.allclose(results[True][1], results[False][1], rtol=1e-3, atol=1e-5)
+  assert results[True][2:] == results[False][2:] == (20, 20)
+
+
 # =============================================================================== plumbing
 def test_ops_are_cuda_graph_capturable():
   """GAE + gather + loss captured once and replayed on new data in the same buffers."""
