@@ -8,14 +8,45 @@ accelerated scope — and is provided so `make_ppo_runner` stays a drop-in.
 """
 from abc import ABC, abstractmethod
 
+import numpy as np
+import torch
+
 _FORWARDED = frozenset(("env", "policy", "horizon", "nsteps", "step_count", "nenvs",
                         "is_exhausted"))
 
 
-class EnvRunner:
-  """Steps `env` with `policy` for `horizon` steps per yielded rollout."""
+class _ResidentRollout:
+  """Preallocated [horizon, ...] tensors on `device`, filled one step at a time
+  (SURVEY.md §8f rank 3): the rollout is born in HBM instead of being stacked from T host
+  lists (`np.asarray`, derl/runners/onpolicy.py:20-27) and uploaded afterwards."""
 
-  def __init__(self, env, policy, horizon, nsteps=None, time_limit=None):
+  def __init__(self, horizon, device):
+    self.horizon, self.device = horizon, torch.device(device)
+    self.buffers = {}
+
+  def put(self, key, step, value):
+    arr = np.asarray(value)
+    if arr.dtype == object or arr.dtype.kind in "USV":
+      return False
+    buf = self.buffers.get(key)
+    if buf is None or buf.shape[1:] != arr.shape or buf.dtype != torch.from_numpy(arr[None]).dtype:
+      buf = self.buffers[key] = torch.empty((self.horizon,) + arr.shape,
+                                            dtype=torch.from_numpy(arr[None]).dtype,
+                                            device=self.device)
+    buf[step].copy_(torch.from_numpy(np.ascontiguousarray(arr)), non_blocking=True)
+    return True
+
+
+class EnvRunner:
+  """Steps `env` with `policy` for `horizon` steps per yielded rollout.
+
+  `resident_device` (extension, default None = reference behaviour): write every numeric
+  per-step value straight into preallocated device tensors; `next_observations` is then not
+  collected (nothing on the PPO path reads it) and `infos` stays a host list.
+  """
+
+  def __init__(self, env, policy, horizon, nsteps=None, time_limit=None, resident_device=None):
+    self.resident_device = resident_device
     self.env, self.policy, self.horizon = env, policy, horizon
     self.nsteps = int(nsteps)
     if time_limit is not None and getattr(env.unwrapped, "nenvs", None) is not None:
@@ -41,21 +72,32 @@ class EnvRunner:
       self.episode_length = 0
     while not self.is_exhausted():
       rollout = {}
-      put = lambda key, val: rollout.setdefault(key, []).append(val)
-      for _ in range(self.horizon):
+      resident = None
+      if self.resident_device is not None:
+        resident = _ResidentRollout(self.horizon, self.resident_device)
+
+      def put(key, val, step):
+        if resident is not None and key == "next_observations":
+          return
+        if resident is not None and resident.put(key, step, val):
+          rollout[key] = resident.buffers[key]
+        else:
+          rollout.setdefault(key, []).append(val)
+
+      for step in range(self.horizon):
         act = self.policy.act(obs)
-        put("observations", obs)
+        put("observations", obs, step)
         if "actions" not in act:
           raise ValueError("result of policy.act must contain 'actions' "
                            f"but has keys {list(act.keys())}")
         for key, val in act.items():
-          put(key, val)
+          put(key, val, step)
         next_obs, reward, done, info = self.env.step(act["actions"])
         self.episode_length += 1
-        put("rewards", reward)
-        put("resets", done)
-        put("infos", info)
-        put("next_observations", next_obs)
+        put("rewards", reward, step)
+        put("resets", done, step)
+        put("infos", info, step)
+        put("next_observations", next_obs, step)
         # batched envs auto-reset; a single env is reset here (env_runner.py:58-65)
         if self.nenvs is None and (done or self.episode_length == self.time_limit):
           obs = self.env.reset()

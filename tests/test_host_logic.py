@@ -181,3 +181,59 @@ def test_synthetic_rollout_shapes_match_env_runner_layout():
   src = d.SyntheticRolloutRunner(policy=None, kind="mujoco", nenvs=None, horizon=16, nsteps=32,
                                  device="cpu")
   assert len(list(src.run())) == 2 and src.step_count == 32 and src.is_exhausted()
+
+
+class CountingEnv:
+  """4 batched toy envs: observation = step counter, episode ends every 3 steps."""
+  nenvs = 4
+
+  def __init__(self):
+    self.t = 0
+
+  @property
+  def unwrapped(self):
+    return self
+
+  def reset(self):
+    self.t = 0
+    return np.full((4, 2), self.t, np.float32)
+
+  def step(self, actions):
+    self.t += 1
+    obs = np.full((4, 2), self.t, np.float32)
+    return obs, np.arange(4, dtype=np.float64) + self.t, np.full(4, self.t % 3 == 0), [{}] * 4
+
+
+class EchoPolicy:
+  def act(self, obs, state=None, update_state=True, training=False):
+    return dict(actions=np.zeros(4, np.int64), log_prob=np.zeros(4, np.float32),
+                values=np.asarray(obs)[:, :1] * 0.5)
+
+  def is_recurrent(self):
+    return False
+
+
+def test_env_runner_list_and_resident_modes_agree():
+  """EnvRunner(resident_device=...) fills preallocated [T, N, ...] tensors step by step and
+  yields the same rollout as the reference-style per-step lists (minus next_observations)."""
+  plain = next(d.EnvRunner(CountingEnv(), EchoPolicy(), horizon=5, nsteps=40).run())
+  runner = d.EnvRunner(CountingEnv(), EchoPolicy(), horizon=5, nsteps=40, resident_device="cpu")
+  gen = runner.run()
+  resident = next(gen)
+  assert runner.step_count == 20 and not runner.is_exhausted()
+  assert "next_observations" in plain and "next_observations" not in resident
+  assert isinstance(resident["infos"], list) and len(resident["infos"]) == 5
+  for key in ("observations", "actions", "log_prob", "values", "rewards", "resets"):
+    want = np.asarray(plain[key])
+    assert isinstance(resident[key], torch.Tensor)
+    np.testing.assert_array_equal(resident[key].numpy(), want)
+    assert resident[key].numpy().dtype == want.dtype
+  np.testing.assert_array_equal(resident["state"]["latest_observations"],
+                                plain["state"]["latest_observations"])
+  second = next(gen)
+  assert float(second["observations"][0, 0, 0]) == 5.0 and runner.is_exhausted()
+  with pytest.raises(ValueError, match="must contain 'actions'"):
+    class NoActions(EchoPolicy):
+      def act(self, obs, **kw):
+        return dict(values=np.zeros((4, 1), np.float32))
+    next(d.EnvRunner(CountingEnv(), NoActions(), 2, 10).run())
