@@ -31,6 +31,8 @@ SIGNATURES = {
     "derl_b200_moments_workspace_bytes": (_size, [_i64]),
     "derl_b200_moments": (_int, [_ptr, _i64, _ptr, _ptr, _size, _ptr]),
     "derl_b200_gather_rows": (_int, [_ptr, _i64, _i64, _ptr, _i64, _i64, _ptr, _ptr]),
+    "derl_b200_gather_rows_upload": (_int, [_ptr, _i64, _i64, _ptr, _i64, _i64, _ptr, _ptr, _int,
+                                            _ptr]),
     "derl_b200_gather_columns": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _ptr,
                                         _ptr, _size, _ptr]),
     "derl_b200_ppo_loss_workspace_bytes": (_size, [_i64]),

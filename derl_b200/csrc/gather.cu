@@ -19,15 +19,21 @@ namespace {
 // ------------------------------------------------------------------ TMA bulk row gather
 constexpr int kStageBytes = 28672;  // >= one 28224-B frame stack; multiple of 128
 constexpr int kStages = 8;          // 8 * 28 KiB = 224 KiB of the 227 KiB a CTA may own
-constexpr size_t kGatherSmem = (size_t)kStages * kStageBytes + 8 * kStages;
+constexpr size_t kGatherSmem = (size_t)kStages * kStageBytes + 16 * kStages;
 
+// `mirror` (optional): a second destination indexed like the SOURCE — every gathered row is
+// also written to mirror[src_row].  With `src` in pinned host memory this is the first-epoch
+// upload path: the minibatch and the resident device copy of the rollout are both filled by
+// the one pass over PCIe (a permutation's minibatches partition the rollout).
 __global__ void __launch_bounds__(32, 1)
 gather_rows_tma_kernel(const uint8_t* __restrict__ src, long long row_bytes,
                        const long long* __restrict__ perm, long long start, long long count,
-                       uint8_t* __restrict__ dst, int chunk_bytes, int chunks_per_row) {
+                       uint8_t* __restrict__ dst, uint8_t* __restrict__ mirror, int chunk_bytes,
+                       int chunks_per_row) {
   extern __shared__ __align__(128) uint8_t smem[];
   if (threadIdx.x != 0) return;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  long long* stage_row = reinterpret_cast<long long*>(full + kStages);
 #pragma unroll
   for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
   mbar_fence_init();
@@ -47,6 +53,7 @@ gather_rows_tma_kernel(const uint8_t* __restrict__ src, long long row_bytes,
     const long long q = u % chunks_per_row;
     const int s = (int)(k % kStages);
     const uint32_t bytes = unit_bytes(q);
+    stage_row[s] = src_row;
     mbar_expect_tx(&full[s], bytes);
     bulk_g2s(smem + (size_t)s * kStageBytes, src + src_row * row_bytes + q * chunk_bytes, bytes,
              &full[s]);
@@ -66,6 +73,10 @@ gather_rows_tma_kernel(const uint8_t* __restrict__ src, long long row_bytes,
     const long long u = first + i * step;
     const long long j = u / chunks_per_row, q = u % chunks_per_row;
     bulk_s2g(dst + j * row_bytes + q * chunk_bytes, smem + (size_t)s * kStageBytes, unit_bytes(q));
+    if (mirror != nullptr) {
+      bulk_s2g(mirror + stage_row[s] * row_bytes + q * chunk_bytes, smem + (size_t)s * kStageBytes,
+               unit_bytes(q));
+    }
     bulk_commit();
     if (i >= 1 && issued < mine) {
       bulk_wait_read<1>();  // store of unit i-1 has drained its stage -> refill it
@@ -183,9 +194,9 @@ using namespace derl;
 
 extern "C" {
 
-int derl_b200_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes,
-                          const int64_t* perm, int64_t start, int64_t count, void* dst,
-                          void* stream) {
+static int gather_rows_impl(const void* src, int64_t n_src_rows, int64_t row_bytes,
+                            const int64_t* perm, int64_t start, int64_t count, void* dst,
+                            void* mirror, int max_ctas, void* stream) {
   DERL_REQUIRE(src && perm && dst, "gather_rows: null pointer");
   DERL_REQUIRE(row_bytes >= 1 && n_src_rows >= 1 && start >= 0 && count >= 0,
                "gather_rows: bad sizes (row_bytes=%lld rows=%lld start=%lld count=%lld)",
@@ -195,7 +206,9 @@ int derl_b200_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes
   if (count == 0) return DERL_OK;
   cudaStream_t st = as_stream(stream);
   const long long* p = reinterpret_cast<const long long*>(perm);
-  const int align = pow2_align((uintptr_t)src, (uintptr_t)dst, row_bytes);
+  const int align = pow2_align((uintptr_t)src | (uintptr_t)mirror, (uintptr_t)dst, row_bytes);
+  DERL_REQUIRE(mirror == nullptr || (align == 16 && row_bytes >= 2048),
+               "gather_rows_upload: rows must be 16-byte multiples of at least 2048 bytes");
   if (align == 16 && row_bytes >= 2048) {
     const int cpr = (int)((row_bytes + kStageBytes - 1) / kStageBytes);
     // equal 16-byte-multiple chunks; the last one takes the remainder
@@ -209,10 +222,11 @@ int derl_b200_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes
     }
     const long long units = count * cpr;
     long long grid = sm_count();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > units) grid = units;
     gather_rows_tma_kernel<<<(unsigned)grid, 32, kGatherSmem, st>>>(
         reinterpret_cast<const uint8_t*>(src), row_bytes, p, start, count,
-        reinterpret_cast<uint8_t*>(dst), (int)chunk, cpr);
+        reinterpret_cast<uint8_t*>(dst), reinterpret_cast<uint8_t*>(mirror), (int)chunk, cpr);
     DERL_LAUNCH_CHECK("gather_rows_tma_kernel");
     return DERL_OK;
   }
@@ -223,6 +237,20 @@ int derl_b200_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes
     case 2: return launch_vec<unsigned short>(src, row_bytes, p, start, count, dst, st);
     default: return launch_vec<uint8_t>(src, row_bytes, p, start, count, dst, st);
   }
+}
+
+int derl_b200_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes,
+                          const int64_t* perm, int64_t start, int64_t count, void* dst,
+                          void* stream) {
+  return gather_rows_impl(src, n_src_rows, row_bytes, perm, start, count, dst, nullptr, 0, stream);
+}
+
+int derl_b200_gather_rows_upload(const void* src_host, int64_t n_src_rows, int64_t row_bytes,
+                                 const int64_t* perm, int64_t start, int64_t count, void* dst,
+                                 void* resident, int max_ctas, void* stream) {
+  DERL_REQUIRE(resident != nullptr, "gather_rows_upload: resident buffer is NULL");
+  return gather_rows_impl(src_host, n_src_rows, row_bytes, perm, start, count, dst, resident,
+                          max_ctas, stream);
 }
 
 int derl_b200_gather_columns(int n_columns, const void* const* src, const int64_t* row_bytes,

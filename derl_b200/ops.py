@@ -173,6 +173,35 @@ def _(src, perm, start, count):
   return src.new_empty((count,) + tuple(src.shape[1:]))
 
 
+@torch.library.custom_op("derl_b200::gather_rows_upload", mutates_args=("resident",),
+                         device_types="cuda")
+def gather_rows_upload(host_ptr: int, perm: Tensor, start: int, count: int, resident: Tensor,
+                       max_ctas: int = 8) -> Tensor:
+  """First-epoch upload gather: rows perm[start:start+count] of a column living in PINNED HOST
+  memory at `host_ptr` (same shape/dtype as `resident`) are copied once over PCIe and written
+  both to the returned minibatch tensor and to `resident[perm[...]]`."""
+  _dense(resident, "resident")
+  _dense(perm, "perm", (torch.int64,))
+  _need(host_ptr != 0 and host_ptr % 16 == 0, "host pointer must be non-null and 16-byte aligned")
+  _need(resident.dim() >= 1 and resident.shape[0] >= 1, "resident must have at least one row")
+  _need(0 <= start and 0 <= count and start + count <= perm.numel(),
+        f"window [{start}, {start + count}) outside perm of {perm.numel()}")
+  out = resident.new_empty((count,) + tuple(resident.shape[1:]))
+  row_bytes = resident[0].numel() * resident.element_size()
+  if count == 0:
+    return out
+  with _device_of(resident, "gather_rows_upload"):
+    _lib.check(_lib.load().derl_b200_gather_rows_upload(
+        _VP(host_ptr), resident.shape[0], row_bytes, _p(perm), start, count, _p(out),
+        _p(resident), int(max_ctas), _stream(resident)), "gather_rows_upload")
+  return out
+
+
+@gather_rows_upload.register_fake
+def _(host_ptr, perm, start, count, resident, max_ctas=8):
+  return resident.new_empty((count,) + tuple(resident.shape[1:]))
+
+
 @torch.library.custom_op("derl_b200::gather_columns", mutates_args=(), device_types="cuda")
 def gather_columns(columns: List[Tensor], perm: Tensor, start: int, count: int,
                    moments_col: int = -1) -> List[Tensor]:

@@ -17,6 +17,7 @@ import torch
 
 from .. import _lib, ops  # noqa: F401
 from .env_runner import EnvRunner, RunnerWrapper
+from .host_column import HostColumn, eligible as _lazy_eligible
 from .summary import PeriodicSummaries
 from .trajectory_transforms import (GAE, MergeTimeBatch, NormalizeAdvantages, policy_device,
                                     to_device)
@@ -34,13 +35,16 @@ class TransformInteractions(RunnerWrapper):
   stay NumPy object arrays on the host.
   """
 
-  def __init__(self, runner, transforms=None, asarray=True):
+  def __init__(self, runner, transforms=None, asarray=True, lazy_upload=True):
     super().__init__(runner)
     self.transforms = transforms or []
     self.asarray = asarray
+    # wide columns handed over in PINNED host memory are uploaded by the first epoch's gathers
+    # (overlapped with the update) instead of one blocking copy; see runners/host_column.py
+    self.lazy_upload = lazy_upload
 
   def _densify(self, key, val, device):
-    if isinstance(val, torch.Tensor):
+    if isinstance(val, (torch.Tensor, HostColumn)):
       return val
     try:
       arr = np.asarray(val)
@@ -48,6 +52,10 @@ class TransformInteractions(RunnerWrapper):
       raise ValueError(f"cannot convert value under key '{key}' to np.ndarray")
     if arr.dtype == object or arr.dtype.kind in "USV":
       return arr
+    if self.lazy_upload and key == "observations":
+      host = _lazy_eligible(arr)
+      if host is not None:
+        return HostColumn(host, device)
     return to_device(arr, device)
 
   def run(self, obs=None):
@@ -65,7 +73,7 @@ def _row_bytes(t):
   return (t[0].numel() * t.element_size()) if t.shape[0] > 0 else 0
 
 
-def gather_minibatch(interactions, perm, start, count, host_perm=None):
+def gather_minibatch(interactions, perm, start, count, host_perm=None, perm_ready=None):
   """dict of rows perm[start:start+count] of every array in `interactions`.
 
   Wide columns (frame stacks) use the TMA row gather, all narrow columns share one launch
@@ -75,6 +83,8 @@ def gather_minibatch(interactions, perm, start, count, host_perm=None):
   for key, val in interactions.items():
     if key == "state":
       out[key] = val
+    elif isinstance(val, HostColumn):
+      out[key] = val.gather(perm, start, count, perm_ready)
     elif isinstance(val, torch.Tensor):
       if not val.is_cuda:
         raise TypeError(f"interactions['{key}'] is a CPU tensor; the rollout must be resident "
@@ -131,6 +141,9 @@ class IterateWithMinibatches(RunnerWrapper):
                    if isinstance(v, torch.Tensor) and v.is_cuda), None)
     if device is None:
       raise TypeError("shuffle_interactions needs the rollout resident on the GPU")
+    for key, val in interactions.items():
+      if isinstance(val, HostColumn):
+        interactions[key] = val.materialize()
     perm = IterateWithMinibatches._upload(order, device)
     interactions.update(gather_minibatch(interactions, perm, 0, size, host_perm=order))
 
@@ -142,19 +155,22 @@ class IterateWithMinibatches(RunnerWrapper):
       if device is None:
         raise TypeError("IterateWithMinibatches needs the rollout resident on the GPU "
                         "(wrap the runner in TransformInteractions first)")
-      order, perm = None, None
+      order, perm, perm_ready = None, None, None
       for _ in range(self.num_epochs):
         if self.shuffle_before_epoch:
           draw = np.random.permutation(size)                  # same RNG stream as :46
           order = draw if order is None else order[draw]      # compose: shuffles were in place
           perm = self._upload(order, device)
+          perm_ready = torch.cuda.current_stream(device).record_event()
         elif perm is None:
           order = np.arange(size)
           perm = self._upload(order, device)
+          perm_ready = torch.cuda.current_stream(device).record_event()
         mbsize = size // self.num_minibatches
         for start in range(0, size, mbsize):
           count = min(start + mbsize, size) - start
-          yield gather_minibatch(interactions, perm, start, count, host_perm=order)
+          yield gather_minibatch(interactions, perm, start, count, host_perm=order,
+                                 perm_ready=perm_ready)
 
 
 def ppo_runner_wrap(runner, gamma=0.99, lambda_=0.95, num_epochs=3, num_minibatches=4):

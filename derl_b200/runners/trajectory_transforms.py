@@ -38,7 +38,8 @@ def to_device(value, device):
 
 
 def _is_array(value):
-  return isinstance(value, (np.ndarray, torch.Tensor))
+  from .host_column import HostColumn
+  return isinstance(value, (np.ndarray, torch.Tensor, HostColumn))
 
 
 class GAE:
@@ -172,6 +173,8 @@ class Take:
     for key, val in trajectory.items():
       if key == "state":
         continue
+      if hasattr(val, "materialize"):   # HostColumn: upload, then index on the device
+        val = val.materialize()
       if isinstance(val, torch.Tensor):
         index = torch.as_tensor(np.asarray(self.indices), device=val.device)
         if index.ndim == 0:

@@ -110,6 +110,20 @@ int derl_b200_gather_rows(const void* src_dev, int64_t n_src_rows, int64_t row_b
                           const int64_t* perm_dev, int64_t start, int64_t count,
                           void* dst_dev, void* stream);
 
+/* First-epoch upload: `src_host` is PINNED HOST memory (device-accessible under UVA, e.g.
+ * cudaHostAlloc / torch pin_memory) holding the whole column; every gathered row is written
+ * twice — to dst[j] (the minibatch) and to resident_dev[perm[start+j]] (the device copy of the
+ * column, at its original position).  Because the minibatches of one epoch partition the
+ * permutation, running this for every minibatch of the first epoch uploads the rollout exactly
+ * once, overlapped with the update of the previous minibatch when issued on a side stream,
+ * instead of a blocking 14.8 GB cudaMemcpy up front (reference: `torch.from_numpy(...).to(device)`
+ * per minibatch, derl/models.py:79-88).  max_ctas > 0 limits the grid (the copy is PCIe-bound;
+ * a few CTAs saturate it and leave the other SMs to the concurrent update).  Rows must be
+ * 16-byte multiples of at least 2048 bytes. */
+int derl_b200_gather_rows_upload(const void* src_host, int64_t n_src_rows, int64_t row_bytes,
+                                 const int64_t* perm_dev, int64_t start, int64_t count,
+                                 void* dst_dev, void* resident_dev, int max_ctas, void* stream);
+
 /* derl_b200_gather_columns: up to DERL_MAX_COLUMNS narrow columns (actions, log_prob,
  * advantages, value_targets, values, rewards, resets ...) in one launch.  Column c has
  * row_bytes[c] bytes per sample.  If moments_col >= 0 that column must be float32 with

@@ -334,6 +334,68 @@ def test_minibatch_pipeline_matches_reference_golden(golden):
     np.testing.assert_allclose(np.concatenate(advs), c["mb_advantages"], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("nmb,shuffle", [(4, True), (3, True), (4, False)])
+def test_first_epoch_upload_from_pinned_host_memory(nmb, shuffle, monkeypatch):
+  """Observations handed over in pinned host memory become a HostColumn: the first epoch's
+  minibatches are pulled over PCIe by the gather kernel (side stream) and mirrored into the
+  device-resident copy; later epochs read HBM.  Every minibatch is bit-identical to the
+  all-resident pipeline and the resident copy ends up equal to the host array."""
+  from derl_b200.runners import host_column
+  monkeypatch.setattr(host_column, "MIN_BYTES", 0)
+  nsteps, nenvs = 10, 7   # S = 70: ragged tail for nmb = 3 and 4
+  rng = np.random.RandomState(8)
+  pinned = torch.empty((nsteps, nenvs, 84, 84, 4), dtype=torch.uint8, pin_memory=True)
+  pinned.copy_(torch.from_numpy(rng.randint(0, 256, pinned.shape).astype(np.uint8)))
+  base = dict(actions=rng.randint(0, 4, (nsteps, nenvs)).astype(np.int64),
+              log_prob=rng.standard_normal((nsteps, nenvs)).astype(np.float32),
+              values=rng.standard_normal((nsteps, nenvs, 1)).astype(np.float32),
+              rewards=rng.standard_normal((nsteps, nenvs)), resets=rng.random((nsteps, nenvs)) < .1)
+  last_value = rng.standard_normal((nenvs, 1)).astype(np.float32)
+
+  def batches(observations):
+    rollout = dict(observations=observations, **base,
+                   state=dict(latest_observations=np.zeros((nenvs, 84, 84, 4), np.uint8)))
+
+    class Source:
+      env = type("E", (), {"nenvs": nenvs, "unwrapped": property(lambda s: s)})()
+      policy = ConstPolicy(last_value)
+      horizon, step_count = nsteps, 0
+      nsteps = 1
+
+      def run(self, obs=None):
+        yield dict(rollout)
+
+    inner = d.TransformInteractions(Source(), [d.GAE(Source.policy, normalize=False),
+                                               d.MergeTimeBatch()])
+    runner = d.IterateWithMinibatches(inner, 3, nmb, shuffle_before_epoch=shuffle)
+    np.random.seed(5)
+    seen = {}
+    out = []
+    for batch in runner.run():
+      out.append({k: v.clone() for k, v in batch.items() if isinstance(v, torch.Tensor)})
+    return out
+
+  lazy = batches(pinned.numpy())
+  eager = batches(pinned.numpy().copy())   # pageable copy -> ordinary one-shot upload
+  assert len(lazy) == len(eager) == 3 * len(range(0, 70, 70 // nmb))
+  for a, b in zip(lazy, eager):
+    assert a.keys() == b.keys()
+    for k in a:
+      assert torch.equal(a[k], b[k]), k
+  # direct check of the column object
+  col = host_column.HostColumn(pinned.reshape(70, 84, 84, 4), DEV)
+  perm = cuda(np.random.RandomState(1).permutation(70))
+  parts = [col.gather(perm, lo, min(lo + 24, 70) - lo) for lo in range(0, 70, 24)]
+  assert col.complete
+  torch.cuda.synchronize()
+  assert torch.equal(col.resident.cpu(), pinned.reshape(70, 84, 84, 4))
+  assert torch.equal(torch.cat(parts).cpu(), pinned.reshape(70, 84, 84, 4)[perm.cpu()])
+  # a non-sequential access pattern falls back to one bulk upload
+  col2 = host_column.HostColumn(pinned.reshape(70, 84, 84, 4), DEV)
+  mid = col2.gather(perm, 30, 10)
+  assert col2.complete and torch.equal(mid.cpu(), pinned.reshape(70, 84, 84, 4)[perm.cpu()[30:40]])
+
+
 def test_iterate_without_shuffle_and_too_many_minibatches():
   rollout = dict(observations=torch.arange(10, device=DEV).reshape(10, 1).float(),
                  advantages=torch.arange(10, device=DEV).float(), state=dict(k=1))
