@@ -109,12 +109,34 @@ class NatureCNNBase(nn.Sequential):
   space_to_depth = True   # class-wide switches (tests compare the formulations)
   fused_conv_relu = True
 
-  def _conv_relu(self, hidden, conv, weight=None):
-    """conv + bias + ReLU; one fused cuDNN call on the GPU when the layer allows it."""
-    weight = conv.weight if weight is None else weight
-    bias, stride = conv.bias, conv.stride
-    if weight.shape[2:] != conv.kernel_size:   # re-indexed stem: 2x2 / stride 1
-      stride = (1, 1)
+  @staticmethod
+  def _s2d_weight(conv):
+    """[O, C, 2s, 2s] -> [O, s*s*C, 2, 2]: weights of the equivalent 2x2 / stride-1 conv over
+    the space-to-depth(s) tensor (channel order (i, j, c), like the activations)."""
+    s, out_ch, in_ch = conv.stride[0], conv.out_channels, conv.in_channels
+    weight = conv.weight.view(out_ch, in_ch, 2, s, 2, s).permute(0, 3, 5, 1, 2, 4)
+    return weight.reshape(out_ch, s * s * in_ch, 2, 2).contiguous(
+        memory_format=torch.channels_last)
+
+  @staticmethod
+  def _s2d_ok(conv, height, width):
+    s = conv.stride[0]
+    return (s > 1 and conv.stride == (s, s) and conv.kernel_size == (2 * s, 2 * s)
+            and conv.padding == (0, 0) and conv.dilation == (1, 1) and conv.groups == 1
+            and height % s == 0 and width % s == 0)
+
+  def _conv_relu(self, hidden, conv):
+    """conv + bias + ReLU.  A strided conv with kernel = 2 x stride is evaluated as a 2x2 /
+    stride-1 conv over the space-to-depth activation (same parameters, same sums): cuDNN's
+    strided dgrad for the 4x4/2 layer alone was 34 % of the update, the stride-1 form runs
+    on its fast implicit-GEMM kernels.  On the GPU conv, bias and ReLU are one cuDNN call."""
+    weight, bias, stride = conv.weight, conv.bias, conv.stride
+    if self.space_to_depth and hidden.is_cuda and self._s2d_ok(conv, *hidden.shape[2:]):
+      s, (batch, chans, height, width) = stride[0], hidden.shape
+      blocks = hidden.permute(0, 2, 3, 1).reshape(batch, height // s, s, width // s, s, chans)
+      hidden = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s,
+                                                        s * s * chans).permute(0, 3, 1, 2)
+      weight, stride = self._s2d_weight(conv), (1, 1)
     if (self.fused_conv_relu and hidden.is_cuda and bias is not None and conv.groups == 1
         and conv.dilation == (1, 1) and isinstance(conv.padding, tuple)):
       if hidden.dtype != weight.dtype:         # autocast: run the whole layer in that dtype
@@ -122,32 +144,25 @@ class NatureCNNBase(nn.Sequential):
       return _ConvBiasReLU.apply(hidden, weight, bias, stride, conv.padding)
     return torch.relu(nn.functional.conv2d(hidden, weight, bias, stride, conv.padding))
 
-  def _first_conv_as_space_to_depth(self, frames):
-    """conv(k = 2s, stride s) on NHWC uint8 frames == conv(k = 2, stride 1) on the
-    space-to-depth(s) tensor with s*s*C channels and re-indexed weights (same parameters,
-    same sums).  For the Atari stem (8x8 / 4 over 4 channels) this turns a C=4 convolution,
-    for which cuDNN only has a scalar NHWC engine (13 ms per 16384 frames on B200, 49 % of
-    the whole update), into a C=64 one that runs on tensor cores.  On the GPU the
-    re-indexing, the uint8 -> float cast and the /255 are one pass of the frames_to_s2d
-    kernel (IEEE division: the same input values as the reference's `.float() / 255`).
-    """
+  def _forward_frames(self, frames):
+    """uint8 NHWC frames on the GPU.  The 8x8/4 stem over 4 channels is a 2x2/1 conv over the
+    space-to-depth(4) tensor with 64 channels: cuDNN has only a scalar NHWC engine for C = 4
+    (13 ms per 16384 frames, 49 % of the update before this change) but tensor-core implicit
+    GEMM for C = 64.  Re-indexing, uint8 -> float cast and the /255 are ONE pass of the
+    frames_to_s2d kernel (IEEE division: the reference's `.float() / 255` values exactly)."""
     conv = self[0]
-    batch, height, width, chans = frames.shape
     s = conv.stride[0]
-    if frames.is_cuda and s * chans == 16:
-      from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
-      dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") \
-          else conv.weight.dtype
-      s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0)
+    from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
+    dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") \
+        else conv.weight.dtype
+    s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0).permute(0, 3, 1, 2)
+    weight, bias = self._s2d_weight(conv), conv.bias
+    if self.fused_conv_relu:
+      if s2d.dtype != weight.dtype:
+        weight, bias = weight.to(s2d.dtype), bias.to(s2d.dtype)
+      hidden = _ConvBiasReLU.apply(s2d, weight, bias, (1, 1), (0, 0))
     else:
-      blocks = frames.view(batch, height // s, s, width // s, s, chans)
-      s2d = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s, -1)
-      s2d = s2d.float() / 255
-    s2d = s2d.permute(0, 3, 1, 2)   # NHWC storage seen as NCHW == channels_last
-    weight = conv.weight.view(conv.out_channels, chans, 2, s, 2, s).permute(0, 3, 5, 1, 2, 4)
-    weight = weight.reshape(conv.out_channels, s * s * chans, 2, 2).contiguous(
-        memory_format=torch.channels_last)
-    hidden = self._conv_relu(s2d, conv, weight)
+      hidden = torch.relu(nn.functional.conv2d(s2d, weight, bias))
     layers = list(self.children())[2:]          # after conv-0, relu-0
     while len(layers) >= 2 and isinstance(layers[0], nn.Conv2d) and isinstance(layers[1], nn.ReLU):
       hidden = self._conv_relu(hidden, layers[0])
@@ -158,17 +173,15 @@ class NatureCNNBase(nn.Sequential):
 
   def _s2d_applies(self, inputs):
     conv = self[0]
-    s = conv.stride[0]
     return (self.space_to_depth and self.permute and inputs.is_cuda and inputs.dtype == torch.uint8
-            and inputs.is_contiguous() and conv.stride == (s, s)
-            and conv.kernel_size == (2 * s, 2 * s) and conv.padding == (0, 0)
-            and conv.dilation == (1, 1) and conv.groups == 1
-            and inputs.shape[1] % s == 0 and inputs.shape[2] % s == 0)
+            and inputs.ndim == 4 and inputs.is_contiguous() and conv.bias is not None
+            and self._s2d_ok(conv, inputs.shape[1], inputs.shape[2])
+            and conv.stride[0] * inputs.shape[3] == 16)
 
   def forward(self, inputs):
     inputs, = _collocate(self, [inputs], cast_dtype=False)
     if self._s2d_applies(inputs):
-      return self._first_conv_as_space_to_depth(inputs)
+      return self._forward_frames(inputs)
     if self.permute:
       inputs = inputs.permute(0, 3, 1, 2)   # NHWC storage seen as NCHW == channels_last
     if inputs.dtype == torch.uint8:
