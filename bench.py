@@ -57,6 +57,8 @@ def parse_args():
                  help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
   p.add_argument("--cpu-envs", type=int, default=32,
                  help="envs of the bounded CPU-baseline sample (same horizon/epochs/minibatches)")
+  p.add_argument("--no-s2d-hidden", action="store_true",
+                 help="A/B switch: keep the 4x4/2 conv strided instead of space-to-depth")
   p.add_argument("--no-e2e", action="store_true")
   p.add_argument("--no-alt", action="store_true",
                  help="skip the informational bf16-autocast-network measurement")
@@ -346,6 +348,8 @@ def run_ours(args, rank, world, local):
   torch.backends.cudnn.allow_tf32 = tf32
   torch.backends.cuda.matmul.allow_tf32 = tf32
 
+  if args.no_s2d_hidden:
+    d.NatureCNNBase.space_to_depth_hidden = False
   torch.manual_seed(0)  # identical initial weights on every rank
   model = d.NatureCNNModel([args.nactions, 1])
   if args.net == "bf16":

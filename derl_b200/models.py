@@ -106,7 +106,8 @@ class NatureCNNBase(nn.Sequential):
     self.add_module("flatten", nn.Flatten())
     self.add_module("linear", nn.Linear(height * width * convs[-1].out_channels, 512))
 
-  space_to_depth = True   # class-wide switches (tests compare the formulations)
+  space_to_depth = True          # class-wide switches (tests compare the formulations)
+  space_to_depth_hidden = True   # ... also for strided convs after the stem
   fused_conv_relu = True
 
   @staticmethod
@@ -131,7 +132,8 @@ class NatureCNNBase(nn.Sequential):
     strided dgrad for the 4x4/2 layer alone was 34 % of the update, the stride-1 form runs
     on its fast implicit-GEMM kernels.  On the GPU conv, bias and ReLU are one cuDNN call."""
     weight, bias, stride = conv.weight, conv.bias, conv.stride
-    if self.space_to_depth and hidden.is_cuda and self._s2d_ok(conv, *hidden.shape[2:]):
+    if (self.space_to_depth and self.space_to_depth_hidden and hidden.is_cuda
+        and self._s2d_ok(conv, *hidden.shape[2:])):
       s, (batch, chans, height, width) = stride[0], hidden.shape
       blocks = hidden.permute(0, 2, 3, 1).reshape(batch, height // s, s, width // s, s, chans)
       hidden = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s,
