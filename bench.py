@@ -57,8 +57,10 @@ def parse_args():
                  help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
   p.add_argument("--cpu-envs", type=int, default=32,
                  help="envs of the bounded CPU-baseline sample (same horizon/epochs/minibatches)")
-  p.add_argument("--no-s2d-hidden", action="store_true",
-                 help="A/B switch: keep the 4x4/2 conv strided instead of space-to-depth")
+  p.add_argument("--s2d-hidden", action="store_true",
+                 help="A/B switch: evaluate the 4x4/2 conv in space-to-depth form as well")
+  p.add_argument("--torch-profile", default=None,
+                 help="diagnostic: write a torch.profiler kernel table of one extra step here")
   p.add_argument("--no-e2e", action="store_true")
   p.add_argument("--no-alt", action="store_true",
                  help="skip the informational bf16-autocast-network measurement")
@@ -348,8 +350,8 @@ def run_ours(args, rank, world, local):
   torch.backends.cudnn.allow_tf32 = tf32
   torch.backends.cuda.matmul.allow_tf32 = tf32
 
-  if args.no_s2d_hidden:
-    d.NatureCNNBase.space_to_depth_hidden = False
+  if args.s2d_hidden:
+    d.NatureCNNBase.space_to_depth_hidden = True
   torch.manual_seed(0)  # identical initial weights on every rank
   model = d.NatureCNNModel([args.nactions, 1])
   if args.net == "bf16":
@@ -398,6 +400,16 @@ def run_ours(args, rank, world, local):
       entry["GBps"] = per_elem[name] / ms / 1e6
       entry["frac"] = entry["GBps"] / hbm_peak
     kernels[name] = entry
+
+  if args.torch_profile and rank == 0:   # diagnostic only; never part of a reported number
+    from torch.profiler import ProfilerActivity, profile
+    it = runner.run()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+      one_update(alg, it, nbatches)
+      torch.cuda.synchronize()
+    with open(args.torch_profile, "w") as f:
+      f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45,
+                                        max_name_column_width=90))
 
   # ---- informational: the same update with the network under bf16 autocast
   alt = None

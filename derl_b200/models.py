@@ -107,7 +107,8 @@ class NatureCNNBase(nn.Sequential):
     self.add_module("linear", nn.Linear(height * width * convs[-1].out_channels, 512))
 
   space_to_depth = True          # class-wide switches (tests compare the formulations)
-  space_to_depth_hidden = True   # ... also for strided convs after the stem
+  space_to_depth_hidden = False  # ... also for strided convs after the stem: measured 3 % SLOWER
+                                 # on B200 (two permute copies outweigh cuDNN's strided dgrad)
   fused_conv_relu = True
 
   @staticmethod

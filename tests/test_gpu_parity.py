@@ -628,17 +628,19 @@ def test_space_to_depth_first_conv_equals_plain_formulation():
   model = d.NatureCNNModel([6, 1])
   frames = torch.randint(0, 256, (37, 84, 84, 4), dtype=torch.uint8, device=DEV)
   outs = {}
-  for s2d, fused in ((True, True), (True, False), (False, False)):
-    d.NatureCNNBase.space_to_depth, d.NatureCNNBase.fused_conv_relu = s2d, fused
+  for s2d, fused in ((True, True), (True, False), (False, False), ("hidden", True)):
+    d.NatureCNNBase.space_to_depth, d.NatureCNNBase.fused_conv_relu = bool(s2d), fused
+    d.NatureCNNBase.space_to_depth_hidden = s2d == "hidden"
     model.zero_grad()
     logits, values = model(frames)
     (logits.square().sum() + values.sum()).backward()
     outs[s2d, fused] = (logits.detach().clone(), values.detach().clone(),
                         [p.grad.clone() for p in model.parameters()])
   d.NatureCNNBase.space_to_depth = d.NatureCNNBase.fused_conv_relu = True
+  d.NatureCNNBase.space_to_depth_hidden = False
   torch.backends.cudnn.allow_tf32 = True
   plain = outs[False, False]
-  for key in ((True, True), (True, False)):
+  for key in ((True, True), (True, False), ("hidden", True)):
     for a, b in zip(outs[key][:2], plain[:2]):
       assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), key
     for a, b in zip(outs[key][2], plain[2]):
