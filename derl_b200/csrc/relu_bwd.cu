@@ -1,0 +1,187 @@
+// K5 — fused ReLU backward + bias gradient for channels-last activations.
+//
+// In the reference's autograd graph (nn.ReLU after each nn.Conv2d, derl/models.py:102-109)
+// the backward of every conv layer runs threshold_backward over the activation gradient and
+// then cuDNN's convolution_backward re-reads the result once more just to sum it into the bias
+// gradient.  Both are pure HBM passes over [B*H*W, C] tensors (C = 32 / 64 channels innermost
+// in channels-last layout); this kernel does them in one:
+//     grad_pre[r, c] = out[r, c] > 0 ? grad_out[r, c] : 0          (written once)
+//     bias_grad[c]   = sum_r grad_pre[r, c]                        (float32 accumulate)
+// 3 x sizeof(T) bytes per element instead of 4 x, and one launch instead of two.  The
+// cross-block sum uses per-block partials reduced by the last block in fixed order
+// (deterministic, no float atomics).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace derl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 1184;  // 148 SMs x 8
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using type = float4;
+  static __device__ __forceinline__ void unpack(const float4& v, float (&f)[4]) {
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ float4 pack(const float (&f)[4]) {
+    return make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  using type = uint2;
+  static __device__ __forceinline__ void unpack(const uint2& v, float (&f)[4]) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ uint2 pack(const float (&f)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<const unsigned*>(&a);
+    v.y = *reinterpret_cast<const unsigned*>(&b);
+    return v;
+  }
+};
+template <>
+struct Vec4<__half> {
+  using type = uint2;
+  static __device__ __forceinline__ void unpack(const uint2& v, float (&f)[4]) {
+    const __half2 a = *reinterpret_cast<const __half2*>(&v.x);
+    const __half2 b = *reinterpret_cast<const __half2*>(&v.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ uint2 pack(const float (&f)[4]) {
+    const __half2 a = __floats2half2_rn(f[0], f[1]);
+    const __half2 b = __floats2half2_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<const unsigned*>(&a);
+    v.y = *reinterpret_cast<const unsigned*>(&b);
+    return v;
+  }
+};
+
+// quads = C / 4 divides kThreads; thread t owns channel quad (t % quads) of rows t / quads + k * rpb
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
+                     T* __restrict__ grad_pre, float* __restrict__ bias_grad, long long rows,
+                     int quads, float* __restrict__ partials, unsigned* __restrict__ ticket) {
+  using V = typename Vec4<T>::type;
+  __shared__ float4 red[kThreads];
+  __shared__ int is_last;
+  const int quad = threadIdx.x % quads;
+  const int rpb = kThreads / quads;  // rows per block pass
+  const V* g = reinterpret_cast<const V*>(grad_out);
+  const V* o = reinterpret_cast<const V*>(out);
+  V* p = reinterpret_cast<V*>(grad_pre);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = (long long)blockIdx.x * rpb + threadIdx.x / quads; r < rows;
+       r += (long long)gridDim.x * rpb) {
+    const long long at = r * quads + quad;
+    float gv[4], ov[4];
+    Vec4<T>::unpack(__ldg(g + at), gv);
+    Vec4<T>::unpack(__ldg(o + at), ov);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gv[k] = ov[k] > 0.f ? gv[k] : 0.f;
+      acc[k] += gv[k];
+    }
+    p[at] = Vec4<T>::pack(gv);
+  }
+  red[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  __syncthreads();
+  if (threadIdx.x < quads) {  // fixed-order sum over the block's row slots
+    float4 s = red[threadIdx.x];
+    for (int k = 1; k < rpb; ++k) {
+      const float4 v = red[threadIdx.x + k * quads];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(partials)[(size_t)blockIdx.x * quads + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < quads) {  // last block: sum the per-block partials in block order
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partials) + (size_t)b * quads +
+                              threadIdx.x);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    reinterpret_cast<float4*>(bias_grad)[threadIdx.x] =
+        make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+  }
+}
+
+template <typename T>
+int launch(const void* grad_out, const void* out, void* grad_pre, float* bias_grad,
+           long long rows, int channels, void* workspace, cudaStream_t st) {
+  const int quads = channels / 4;
+  const int rpb = kThreads / quads;
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  unsigned* ticket = reinterpret_cast<unsigned*>(workspace);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kTicketBytes);
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  relu_bwd_bias_kernel<T><<<(unsigned)blocks, kThreads, 0, st>>>(
+      reinterpret_cast<const T*>(grad_out), reinterpret_cast<const T*>(out),
+      reinterpret_cast<T*>(grad_pre), bias_grad, rows, quads, partials, ticket);
+  DERL_LAUNCH_CHECK("relu_bwd_bias_kernel");
+  return DERL_OK;
+}
+
+}  // namespace
+}  // namespace derl
+
+using namespace derl;
+
+extern "C" size_t derl_b200_relu_bwd_bias_workspace_bytes(int64_t channels) {
+  if (channels < 4) channels = 4;
+  return kTicketBytes + (size_t)kMaxBlocks * (size_t)channels * sizeof(float);
+}
+
+extern "C" int derl_b200_relu_bwd_bias(const void* grad_out, const void* out, void* grad_pre,
+                                       float* bias_grad, int64_t rows, int64_t channels,
+                                       int dtype, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  DERL_REQUIRE(grad_out && out && grad_pre && bias_grad && workspace,
+               "relu_bwd_bias: null pointer");
+  DERL_REQUIRE(rows >= 1, "relu_bwd_bias: rows must be >= 1");
+  DERL_REQUIRE(channels >= 4 && channels % 4 == 0 && kThreads % (channels / 4) == 0,
+               "relu_bwd_bias: channels=%lld must be a multiple of 4 with (channels/4) dividing %d",
+               (long long)channels, kThreads);
+  DERL_REQUIRE(dtype >= 0 && dtype <= 2, "relu_bwd_bias: dtype %d not in {0,1,2}", dtype);
+  DERL_REQUIRE((((uintptr_t)grad_out | (uintptr_t)out | (uintptr_t)grad_pre |
+                 (uintptr_t)bias_grad) & 15) == 0, "relu_bwd_bias: pointers must be 16-byte aligned");
+  if (workspace_bytes < derl_b200_relu_bwd_bias_workspace_bytes(channels)) {
+    set_error("relu_bwd_bias: workspace %zu B too small", workspace_bytes);
+    return DERL_E_WORKSPACE;
+  }
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  switch (dtype) {
+    case DERL_DTYPE_BF16:
+      return launch<__nv_bfloat16>(grad_out, out, grad_pre, bias_grad, rows, (int)channels,
+                                   workspace, st);
+    case DERL_DTYPE_F16:
+      return launch<__half>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace, st);
+    default:
+      return launch<float>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace, st);
+  }
+}

@@ -73,10 +73,22 @@ class _ConvBiasReLU(torch.autograd.Function):
     ctx.conf = (stride, padding)
     return out
 
+  fused_backward = True  # ReLU mask + bias gradient in one derl_b200 kernel (K5)
+
   @staticmethod
   def backward(ctx, grad_out):
     inputs, weight, out = ctx.saved_tensors
     stride, padding = ctx.conf
+    chans = out.shape[1]
+    if (_ConvBiasReLU.fused_backward and chans % 4 == 0 and 256 % (chans // 4) == 0
+        and out.is_contiguous(memory_format=torch.channels_last)):
+      from . import ops  # noqa: F401
+      grad_out = grad_out.contiguous(memory_format=torch.channels_last)
+      grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out)
+      grad_in, grad_w, _ = torch.ops.aten.convolution_backward(
+          grad_pre, inputs, weight, None, stride, padding, (1, 1), False, (0, 0), 1,
+          [ctx.needs_input_grad[0], True, False])
+      return grad_in, grad_w, grad_b.to(weight.dtype), None, None
     grad_pre = torch.ops.aten.threshold_backward(grad_out, out, 0)
     grad_in, grad_w, grad_b = torch.ops.aten.convolution_backward(
         grad_pre, inputs, weight, [weight.shape[0]], stride, padding, (1, 1), False, (0, 0), 1,
@@ -170,6 +182,18 @@ class NatureCNNBase(nn.Sequential):
     while len(layers) >= 2 and isinstance(layers[0], nn.Conv2d) and isinstance(layers[1], nn.ReLU):
       hidden = self._conv_relu(hidden, layers[0])
       layers = layers[2:]
+    if (len(layers) == 2 and isinstance(layers[0], nn.Flatten) and isinstance(layers[1], nn.Linear)
+        and hidden.is_contiguous(memory_format=torch.channels_last)):
+      # nn.Flatten orders features (c, h, w); the activations lie (h, w, c) in memory.  Re-index
+      # the linear layer's 1.6 M weights instead of transposing B x 3136 activations (and their
+      # gradients) on every pass: the flatten becomes a view.
+      batch, chans, height, width = hidden.shape
+      linear = layers[1]
+      weight = linear.weight.view(-1, chans, height, width).permute(0, 2, 3, 1).reshape(
+          linear.out_features, -1)
+      flat = hidden.permute(0, 2, 3, 1).reshape(batch, -1)
+      return nn.functional.linear(flat, weight.to(flat.dtype), linear.bias.to(flat.dtype)
+                                  if linear.bias is not None else None)
     for layer in layers:                        # flatten, linear
       hidden = layer(hidden)
     return hidden

@@ -278,6 +278,35 @@ def _(frames, block, dtype, divisor):
                           dtype=dtype)
 
 
+# --------------------------------------------------------------------------- K5: ReLU bwd
+@torch.library.custom_op("derl_b200::relu_bwd_bias", mutates_args=(), device_types="cuda")
+def relu_bwd_bias(grad_out: Tensor, out: Tensor) -> Tuple[Tensor, Tensor]:
+  """(grad_out masked by out > 0, per-channel sum of it as float32) for channels-last
+  [B, C, H, W] tensors — threshold_backward and the bias gradient in one pass."""
+  _need(grad_out.dim() == 4 and grad_out.shape == out.shape, "expected two [B, C, H, W] tensors")
+  _need(grad_out.dtype == out.dtype and out.dtype in _S2D_DTYPES, "unsupported dtype")
+  _need(out.is_contiguous(memory_format=torch.channels_last)
+        and grad_out.is_contiguous(memory_format=torch.channels_last),
+        "relu_bwd_bias needs channels_last tensors")
+  batch, chans, height, width = out.shape
+  grad_pre = torch.empty_like(out)
+  bias_grad = torch.empty(chans, dtype=torch.float32, device=out.device)
+  lib = _lib.load()
+  ws_bytes = lib.derl_b200_relu_bwd_bias_workspace_bytes(chans)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
+  with _device_of(out, "relu_bwd_bias"):
+    _lib.check(lib.derl_b200_relu_bwd_bias(_p(grad_out), _p(out), _p(grad_pre), _p(bias_grad),
+                                           batch * height * width, chans,
+                                           _S2D_DTYPES[out.dtype], _p(ws), ws_bytes,
+                                           _stream(out)), "relu_bwd_bias")
+  return grad_pre, bias_grad
+
+
+@relu_bwd_bias.register_fake
+def _(grad_out, out):
+  return torch.empty_like(out), out.new_empty(out.shape[1], dtype=torch.float32)
+
+
 # --------------------------------------------------------------------------- K3: PPO loss
 def _loss_common(head, values, old_log_prob, advantages, value_targets, old_values):
   ref = head if head is not None else values

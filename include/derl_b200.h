@@ -202,6 +202,18 @@ int derl_b200_frames_to_s2d(const uint8_t* src_dev, int64_t batch, int64_t heigh
                             int64_t width, int64_t channels, int64_t block, void* dst_dev,
                             int dst_dtype, double divisor, void* stream);
 
+/* ------------------------------------------------------------------ K5: ReLU backward + bias grad
+ * One pass over a channels-last activation gradient [rows, channels] (rows = B*H*W):
+ *     grad_pre = out > 0 ? grad_out : 0;   bias_grad[c] = sum over rows of grad_pre[:, c]
+ * Replaces, per conv layer of the reference's NatureCNNBase (derl/models.py:102-109), ATen's
+ * threshold_backward plus the extra read cuDNN's convolution_backward spends on the bias
+ * gradient.  dtype as DERL_DTYPE_*; bias_grad is float32; channels % 4 == 0 and channels/4
+ * must divide 256; deterministic.  workspace >= derl_b200_relu_bwd_bias_workspace_bytes(C). */
+size_t derl_b200_relu_bwd_bias_workspace_bytes(int64_t channels);
+int derl_b200_relu_bwd_bias(const void* grad_out_dev, const void* out_dev, void* grad_pre_dev,
+                            float* bias_grad_dev, int64_t rows, int64_t channels, int dtype,
+                            void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations on HOST arrays (what a NumPy caller such as the reference's
  * TransformInteractions hook holds): the library allocates device scratch, copies in on

@@ -617,6 +617,27 @@ def test_frames_to_s2d_kernel_bit_exact(dtype):
     K.frames_to_s2d(cuda(frames), 2, torch.float32, 255.0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_relu_backward_bias_kernel_vs_aten(dtype):
+  """K5: masked gradient bit-identical to ATen's threshold_backward; bias gradient equal to
+  the float64 column sums to float32 accuracy; deterministic across launches."""
+  gen = torch.Generator(device=DEV).manual_seed(6)
+  for shape in ((37, 32, 20, 20), (5, 64, 9, 9), (3, 64, 7, 7), (1, 4, 1, 1), (300, 128, 3, 5)):
+    out = torch.relu(torch.randn(shape, device=DEV, generator=gen)).to(dtype).contiguous(
+        memory_format=torch.channels_last)
+    grad = torch.randn(shape, device=DEV, generator=gen).to(dtype).contiguous(
+        memory_format=torch.channels_last)
+    grad_pre, bias = K.relu_bwd_bias(grad, out)
+    want = torch.ops.aten.threshold_backward(grad, out, 0)
+    assert torch.equal(grad_pre, want) and grad_pre.stride() == out.stride()
+    want_bias = want.double().sum((0, 2, 3))
+    assert torch.allclose(bias.double(), want_bias, rtol=1e-5, atol=1e-4)
+    again = K.relu_bwd_bias(grad, out)[1]
+    assert torch.equal(again, bias)
+  with pytest.raises(ValueError, match="channels_last"):
+    K.relu_bwd_bias(torch.zeros(2, 8, 3, 3, device=DEV), torch.zeros(2, 8, 3, 3, device=DEV))
+
+
 def test_space_to_depth_first_conv_equals_plain_formulation():
   """NatureCNNBase runs the 8x8/4 stem as a 2x2/1 conv on the space-to-depth tensor with
   re-indexed weights (derl_b200/models.py): same parameters, same function as the
