@@ -2,7 +2,7 @@
 
   python tools/profile_kernels.py                       # plain run (must exit 0 first)
   ncu --set full --clock-control none --import-source on \
-      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns' -c 16 \
+      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns|frames_to_s2d|relu_bwd' -c 40 \
       -o gpurun_out/kernels python tools/profile_kernels.py
 
 Sizes: gather = one 131072-row minibatch out of a 4096x128 frame-stack rollout (14.8 GB,
@@ -85,6 +85,11 @@ def main():
   for dt, nb in ((torch.float32, 5.0), (torch.bfloat16, 3.0)):
     timed(f"frames_to_s2d 16384 {str(dt)[6:]}", lambda: K.frames_to_s2d(frames, 4, dt, 255.0),
           nb * frames.numel())
+  act = torch.relu(torch.randn(32768, 32, 20, 20, device=DEV, generator=gen)).contiguous(
+      memory_format=torch.channels_last)
+  gact = torch.randn_like(act)
+  timed("relu_bwd_bias 32768x32x20x20", lambda: K.relu_bwd_bias(gact, act), 12.0 * act.numel())
+  del act, gact
   cols = [adv.repeat(4), vt.reshape(-1).repeat(4), vold.reshape(-1).repeat(4), old_lp.repeat(4),
           acts.repeat(4)]
   timed("gather_columns 5 cols", lambda: K.gather_columns(cols, perm, mb, mb, 0),
