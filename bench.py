@@ -69,6 +69,21 @@ def parse_args():
   return p.parse_args()
 
 
+def ncu_traffic(kernel_prefix):
+  """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture
+  (profiles/r01_kernel_traffic.json, written from tools/profile_kernels.py at the same
+  131072 x 28224-byte minibatch size), or None."""
+  path = os.path.join(REPO, "profiles", "r01_kernel_traffic.json")
+  if not os.path.exists(path):
+    return None
+  with open(path) as f:
+    table = json.load(f)
+  for name, entry in table.items():
+    if kernel_prefix in name:
+      return entry["dram_read_bytes"] + entry["dram_write_bytes"]
+  return None
+
+
 def peaks():
   path = os.path.join(REPO, "MEASURED_PEAKS.json")
   if os.path.exists(path):
@@ -385,8 +400,10 @@ def run_ours(args, rank, world, local):
     n, ms = ktimes["gather_rows"]
     bytes_per_launch = (8 + 2 * OBS_ROW_BYTES) * mb_rows
     achieved = bytes_per_launch / ms / 1e6
+    traffic = ncu_traffic("gather_rows_tma_kernel") if (nenvs, horizon, args.minibatches) == \
+        (4096, 128, 4) else None
     roofline = {"bound": "hbm", "kernel": "gather_rows_tma_kernel", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
                 "launch_ms": ms, "launches_timed": n}
   per_elem = {"gae": 17.0 * horizon * nenvs + 4 * nenvs,
