@@ -21,7 +21,6 @@ roofline = the dominant hand-written kernel (TMA row gather), algorithmic bytes 
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

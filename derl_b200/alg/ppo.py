@@ -94,20 +94,19 @@ class PPOLoss(Loss):
 
   def _fused(self, kind, head, values, actions, old_log_prob, advantages, value_targets,
              old_values, value_loss_coef):
-    if kind == "gaussian" or (kind is None and self._default_kind == "gaussian"):
-      loc, scale = head if head else (None, None)
+    """One launch of the fused kernel; `head`/`values` may be None to skip that side."""
+    if kind == "gaussian":
+      loc, scale = head
       loss, _, _, _, stats = _K.ppo_loss_gaussian(
           loc, scale, values, actions, old_log_prob, advantages, value_targets, old_values,
           self.cliprange, float(value_loss_coef), float(self.entropy_coef))
-    else:
+    else:  # categorical head, or the value-only call (no head at all)
       logits = head[0] if head else None
       loss, _, _, stats = _K.ppo_loss_categorical(
           logits, values, actions, old_log_prob, advantages, value_targets, old_values,
           self.cliprange, float(value_loss_coef), float(self.entropy_coef))
     self.last_stats = stats.detach()
     return loss
-
-  _default_kind = "categorical"
 
   def _log(self, tag_prefix, keys):
     for key in keys:

@@ -63,6 +63,22 @@ def test_no_device_fails_loudly_instead_of_falling_back():
     _lib.check(lib.derl_b200_device_ok(), "device_ok")
 
 
+def test_plain_c_caller_links_and_runs(tmp_path):
+  """tests/abi_smoke.c compiled with gcc against include/derl_b200.h + libderl_b200.so: on a
+  B200 it must report bit-identical GAE, without a GPU it must fail with DERL_E_NO_DEVICE."""
+  import subprocess
+  exe = tmp_path / "abi_smoke"
+  pkg = os.path.join(REPO, "derl_b200")
+  subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-std=c99",
+                  os.path.join(REPO, "tests", "abi_smoke.c"), "-I", os.path.join(REPO, "include"),
+                  "-L", pkg, "-lderl_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)], check=True)
+  proc = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+  if torch.cuda.is_available():
+    assert proc.returncode == 0 and "bit-identical" in proc.stdout, proc.stdout + proc.stderr
+  else:
+    assert proc.returncode == 2 and "no CPU fallback" in proc.stdout, proc.stdout + proc.stderr
+
+
 def test_product_never_imports_the_oracle():
   """oracle/ is test infrastructure: nothing under derl_b200/ may reference it."""
   pkg = os.path.join(REPO, "derl_b200")

@@ -369,7 +369,6 @@ def test_first_epoch_upload_from_pinned_host_memory(nmb, shuffle, monkeypatch):
                                                d.MergeTimeBatch()])
     runner = d.IterateWithMinibatches(inner, 3, nmb, shuffle_before_epoch=shuffle)
     np.random.seed(5)
-    seen = {}
     out = []
     for batch in runner.run():
       out.append({k: v.clone() for k, v in batch.items() if isinstance(v, torch.Tensor)})
