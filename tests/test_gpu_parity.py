@@ -756,6 +756,12 @@ def test_ops_are_cuda_graph_capturable():
   assert captured[0].item() == want[0].item() and torch.equal(captured[1], want[1])
 
 
+def test_plain_c_caller_of_the_abi(tmp_path):
+  """gcc-compiled tests/abi_smoke.c (no Python in the loop) gets bit-identical GAE."""
+  import test_abi
+  test_abi.test_plain_c_caller_links_and_runs(tmp_path)
+
+
 def test_launch_counter_counts_our_kernels():
   before = _lib.launch_count()
   K.moments(torch.ones(100, device=DEV))
