@@ -9,6 +9,7 @@
 // one thread moves one run — fully coalesced writes, 128-B coalesced read segments.  HBM-bound: 1 B read + sizeof(out) B written per element.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -26,21 +27,33 @@ __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float x) {
 template <>
 __device__ __forceinline__ __half to_out<__half>(float x) { return __float2half_rn(x); }
 
-// One thread per 16-byte (j, c) run, enumerated in DESTINATION order t = ((b*HY + Y)*WX + X)*s + i:
-// a warp writes 32 consecutive runs (2 KiB fp32, fully coalesced) and reads s row segments of
-// 32/s consecutive runs each.  Index arithmetic is one 32-bit division per thread.
-template <typename OT, typename IT>
+// One thread per 16-byte (j, c) run.  The s source rows of one (b, Y) block row are contiguous
+// in memory (s * WX runs) and so is their destination: the whole transform is a [s x WX] ->
+// [WX x s] transpose of 16-byte runs inside each such group.  Threads enumerate runs in SOURCE
+// order (kSrcOrder: one contiguous, sector-aligned read stream; each run is written as full
+// 32-byte sectors) or in destination order (fully coalesced writes, strided 128-B reads).
+template <typename OT, typename IT, bool kSrcOrder>
 __global__ void __launch_bounds__(256)
 frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, IT granules, IT wx,
                      int log2s, float divisor) {
   const IT stride = (IT)gridDim.x * blockDim.x;
   const float recip = __frcp_rn(divisor);
   const IT smask = ((IT)1 << log2s) - 1;
-  for (IT t = (IT)blockIdx.x * blockDim.x + threadIdx.x; t < granules; t += stride) {
-    const IT i = t & smask, q = t >> log2s;
-    const IT r = q / wx;             // b*HY + Y
-    const IT X = q - r * wx;
-    const uint4 raw = __ldg(src + (((r << log2s) + i) * wx + X));
+  for (IT t0 = (IT)blockIdx.x * blockDim.x + threadIdx.x; t0 < granules; t0 += stride) {
+    IT t, from;
+    if (kSrcOrder) {
+      const IT group = t0 / (wx << log2s), r = t0 - group * (wx << log2s);
+      const IT i = r / wx, X = r - i * wx;
+      from = t0;
+      t = group * (wx << log2s) + (X << log2s) + i;
+    } else {
+      const IT i = t0 & smask, q = t0 >> log2s;
+      const IT r = q / wx;             // b*HY + Y
+      const IT X = q - r * wx;
+      from = ((r << log2s) + i) * wx + X;
+      t = t0;
+    }
+    const uint4 raw = __ldg(src + from);
     const unsigned words[4] = {raw.x, raw.y, raw.z, raw.w};
     alignas(16) OT vals[16];
 #pragma unroll
@@ -76,12 +89,16 @@ int launch(const void* src, void* dst, long long granules, int wx, int s, float 
   while ((1 << log2s) < s) ++log2s;
   const uint4* in = reinterpret_cast<const uint4*>(src);
   OT* out = reinterpret_cast<OT*>(dst);
-  if (granules < (1ll << 31)) {
-    frames_to_s2d_kernel<OT, unsigned><<<(unsigned)blocks, 256, 0, st>>>(
+  static const bool dst_order = getenv("DERL_FRAMES_DST_ORDER") != nullptr;  // tuning knob
+  if (granules >= (1ll << 31)) {
+    frames_to_s2d_kernel<OT, unsigned long long, true><<<(unsigned)blocks, 256, 0, st>>>(
+        in, out, (unsigned long long)granules, (unsigned long long)wx, log2s, divisor);
+  } else if (dst_order) {
+    frames_to_s2d_kernel<OT, unsigned, false><<<(unsigned)blocks, 256, 0, st>>>(
         in, out, (unsigned)granules, (unsigned)wx, log2s, divisor);
   } else {
-    frames_to_s2d_kernel<OT, unsigned long long><<<(unsigned)blocks, 256, 0, st>>>(
-        in, out, (unsigned long long)granules, (unsigned long long)wx, log2s, divisor);
+    frames_to_s2d_kernel<OT, unsigned, true><<<(unsigned)blocks, 256, 0, st>>>(
+        in, out, (unsigned)granules, (unsigned)wx, log2s, divisor);
   }
   DERL_LAUNCH_CHECK("frames_to_s2d_kernel");
   return DERL_OK;
