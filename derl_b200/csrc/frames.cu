@@ -79,6 +79,58 @@ frames_to_s2d_kernel(const uint4* __restrict__ src, OT* __restrict__ dst, IT gra
   }
 }
 
+// Preferred variant when one group (s * WX runs) fits a CTA: the CTA stages the raw bytes of
+// `gpb` whole groups through shared memory.  Global reads are one contiguous stream (exactly
+// 1 B/element of DRAM traffic), the [s x WX] -> [WX x s] run transpose happens on the 16-byte
+// LDS (<= 2-way bank conflicts), global writes are fully coalesced; all index arithmetic is
+// loop-invariant per thread.
+template <typename OT>
+__global__ void __launch_bounds__(256)
+frames_to_s2d_staged_kernel(const uint4* __restrict__ src, OT* __restrict__ dst,
+                            long long groups, int wx, int log2s, int gpb, float divisor) {
+  __shared__ uint4 stage[256];
+  const int per_group = wx << log2s;
+  const int active = gpb * per_group;
+  const int t = threadIdx.x;
+  const float recip = __frcp_rn(divisor);
+  // destination-order decomposition of this thread's run inside the CTA tile
+  const int g = t / per_group, r = t - g * per_group;
+  const int X = r >> log2s, i = r & ((1 << log2s) - 1);
+  const int from = g * per_group + i * wx + X;
+  for (long long base = (long long)blockIdx.x * gpb; base < groups;
+       base += (long long)gridDim.x * gpb) {
+    const long long left = (groups - base) * per_group;       // runs left from this tile on
+    const int live = left < active ? (int)left : active;
+    const long long run0 = base * per_group;
+    if (t < live) stage[t] = __ldg(src + run0 + t);
+    __syncthreads();
+    if (t < live) {
+      const uint4 raw = stage[from];
+      const unsigned words[4] = {raw.x, raw.y, raw.z, raw.w};
+      alignas(16) OT vals[16];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float f =
+              __uint_as_float(__byte_perm(words[w], 0x4B000000u, 0x7440 + k)) - 8388608.f;
+          float v = f;
+          if (divisor != 1.f) {
+            v = __fmul_rn(f, recip);
+            v = __fmaf_rn(__fmaf_rn(-v, divisor, f), recip, v);
+          }
+          vals[w * 4 + k] = to_out<OT>(v);
+        }
+      }
+      uint4* o = reinterpret_cast<uint4*>(dst + (size_t)(run0 + t) * 16);
+      const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+      for (int c = 0; c < (int)(sizeof(OT) * 16 / 16); ++c) o[c] = v4[c];
+    }
+    __syncthreads();
+  }
+}
+
 template <typename OT>
 int launch(const void* src, void* dst, long long granules, int wx, int s, float divisor,
            cudaStream_t st) {
@@ -89,7 +141,19 @@ int launch(const void* src, void* dst, long long granules, int wx, int s, float 
   while ((1 << log2s) < s) ++log2s;
   const uint4* in = reinterpret_cast<const uint4*>(src);
   OT* out = reinterpret_cast<OT*>(dst);
-  static const bool dst_order = getenv("DERL_FRAMES_DST_ORDER") != nullptr;  // tuning knob
+  static const char* variant = getenv("DERL_FRAMES_VARIANT");  // tuning knob: "dst" | "src"
+  const int per_group = wx * s;
+  if (variant == nullptr && per_group <= 256) {
+    const int gpb = 256 / per_group;
+    const long long groups = granules / per_group;
+    long long grid = (groups + gpb - 1) / gpb;
+    if (grid > cap) grid = cap;
+    frames_to_s2d_staged_kernel<OT><<<(unsigned)grid, 256, 0, st>>>(in, out, groups, wx, log2s,
+                                                                    gpb, divisor);
+    DERL_LAUNCH_CHECK("frames_to_s2d_staged_kernel");
+    return DERL_OK;
+  }
+  const bool dst_order = variant == nullptr || variant[0] == 'd';
   if (granules >= (1ll << 31)) {
     frames_to_s2d_kernel<OT, unsigned long long, true><<<(unsigned)blocks, 256, 0, st>>>(
         in, out, (unsigned long long)granules, (unsigned long long)wx, log2s, divisor);
