@@ -5,6 +5,7 @@ every op body is a pointer hand-off to libderl_b200.so.  The ops are registered 
 only — called with CPU tensors the dispatcher raises, by design (no CPU fallback).
 """
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -28,6 +29,19 @@ def _p(t):
 def _need(cond, msg):
   if not cond:
     raise ValueError(msg)
+
+
+# DERL_B200_CHECK_INDICES=1: validate gather indices on the host (one device sync per call).
+# Off by default: the runner wrappers only ever pass permutations they built themselves.
+CHECK_INDICES = os.environ.get("DERL_B200_CHECK_INDICES", "0") not in ("", "0")
+
+
+def _check_indices(perm, start, count, nrows):
+  if CHECK_INDICES and count > 0:
+    window = perm[start:start + count]
+    lo, hi = int(window.min()), int(window.max())
+    if lo < 0 or hi >= nrows:
+      raise IndexError(f"gather index out of range: [{lo}, {hi}] not within [0, {nrows})")
 
 
 def _dense(t, name, dtypes=None):
@@ -157,6 +171,7 @@ def gather_rows(src: Tensor, perm: Tensor, start: int, count: int) -> Tensor:
   _need(src.dim() >= 1 and src.shape[0] >= 1, "src must have at least one row")
   _need(0 <= start and 0 <= count and start + count <= perm.numel(),
         f"window [{start}, {start + count}) outside perm of {perm.numel()}")
+  _check_indices(perm, start, count, src.shape[0])
   out = src.new_empty((count,) + tuple(src.shape[1:]))
   row_bytes = src[0].numel() * src.element_size()
   if count == 0 or row_bytes == 0:
@@ -214,6 +229,7 @@ def gather_columns(columns: List[Tensor], perm: Tensor, start: int, count: int,
   _need(0 <= start and 0 <= count and start + count <= perm.numel(),
         f"window [{start}, {start + count}) outside perm of {perm.numel()}")
   dev = columns[0].device
+  _check_indices(perm, start, count, min(c.shape[0] for c in columns))
   outs, row_bytes = [], []
   for i, col in enumerate(columns):
     _dense(col, f"columns[{i}]")

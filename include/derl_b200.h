@@ -103,8 +103,8 @@ int derl_b200_moments(const float* x_dev, int64_t count, double* stats_dev,
  * derl_b200_gather_rows: one wide column (frame stacks: row_bytes = 84*84*4 = 28224).
  *   When row_bytes % 16 == 0 and src/dst are 16-byte aligned the rows move through shared
  *   memory with TMA bulk copies (cp.async.bulk, mbarrier-pipelined, persistent CTAs);
- *   otherwise a vectorised LDG/STG kernel is used.  n_src_rows bounds the indices (debug
- *   builds trap on out-of-range; release trusts the caller like NumPy would raise).
+ *   otherwise a vectorised LDG/STG kernel is used.  Indices must lie in [0, n_src_rows): the
+ *   kernels do not check (the Python binding can: DERL_B200_CHECK_INDICES=1).
  */
 int derl_b200_gather_rows(const void* src_dev, int64_t n_src_rows, int64_t row_bytes,
                           const int64_t* perm_dev, int64_t start, int64_t count,

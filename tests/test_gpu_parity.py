@@ -242,6 +242,15 @@ def test_gather_rows_bit_exact(row_shape, dtype, nrows):
   np.testing.assert_array_equal(out, src[idx])
 
 
+def test_gather_index_validation_switch(monkeypatch):
+  from derl_b200 import ops
+  src, bad = cuda(np.arange(40, dtype=np.float32).reshape(10, 4)), cuda(np.array([0, 3, 10]))
+  monkeypatch.setattr(ops, "CHECK_INDICES", True)
+  with pytest.raises(IndexError, match="out of range"):
+    K.gather_rows(src, bad, 0, 3)
+  assert torch.equal(K.gather_rows(src, bad, 0, 2), src[[0, 3]])
+
+
 def test_gather_columns_bit_exact_with_fused_moments():
   rng = np.random.RandomState(21)
   n = 5000
