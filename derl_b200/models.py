@@ -96,6 +96,34 @@ class _ConvBiasReLU(torch.autograd.Function):
     return grad_in, grad_w, grad_b, None, None
 
 
+class _StemConvReLU(torch.autograd.Function):
+  """The 8x8/4 stem + bias + ReLU straight from uint8 frames (derl_b200 K6) forward; backward =
+  K5 (ReLU mask + bias gradient) and the weight gradient of the equivalent space-to-depth conv
+  (K4 re-creates the float frames only here, cuDNN wgrad), mapped back to [32, 4, 8, 8]."""
+
+  @staticmethod
+  def forward(ctx, frames, weight, bias, dtype):
+    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype)
+    out = out.permute(0, 3, 1, 2)   # channels-last storage seen as NCHW
+    ctx.save_for_backward(frames, out)
+    ctx.weight_dtype = weight.dtype
+    return out
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    frames, out = ctx.saved_tensors
+    grad_out = grad_out.contiguous(memory_format=torch.channels_last)
+    grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out)
+    s2d = torch.ops.derl_b200.frames_to_s2d(frames, 4, out.dtype, 255.0).permute(0, 3, 1, 2)
+    shape_only = s2d.new_empty((32, 64, 2, 2)).contiguous(memory_format=torch.channels_last)
+    _, grad_w2, _ = torch.ops.aten.convolution_backward(
+        grad_pre, s2d, shape_only, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1,
+        [False, True, False])
+    # [O, (i, j, c), a, b] -> [O, c, 4a + i, 4b + j]
+    grad_w = grad_w2.reshape(32, 4, 4, 4, 2, 2).permute(0, 3, 4, 1, 5, 2).reshape(32, 4, 8, 8)
+    return None, grad_w.to(ctx.weight_dtype), grad_b, None
+
+
 def _conv_out(size, conv):
   return (size + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) \
       // conv.stride[0] + 1
@@ -118,6 +146,8 @@ class NatureCNNBase(nn.Sequential):
     self.add_module("flatten", nn.Flatten())
     self.add_module("linear", nn.Linear(height * width * convs[-1].out_channels, 512))
 
+  custom_stem = True             # K6: stem conv straight from uint8 frames (needs TF32 allowed
+                                 # or autocast: it is a reduced-precision tensor-core path)
   space_to_depth = True          # class-wide switches (tests compare the formulations)
   space_to_depth_hidden = False  # ... also for strided convs after the stem: measured 3 % SLOWER
                                  # on B200 (two permute copies outweigh cuDNN's strided dgrad)
@@ -168,16 +198,21 @@ class NatureCNNBase(nn.Sequential):
     conv = self[0]
     s = conv.stride[0]
     from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
-    dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") \
-        else conv.weight.dtype
-    s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0).permute(0, 3, 1, 2)
-    weight, bias = self._s2d_weight(conv), conv.bias
-    if self.fused_conv_relu:
-      if s2d.dtype != weight.dtype:
-        weight, bias = weight.to(s2d.dtype), bias.to(s2d.dtype)
-      hidden = _ConvBiasReLU.apply(s2d, weight, bias, (1, 1), (0, 0))
+    autocast = torch.is_autocast_enabled("cuda")
+    dtype = torch.get_autocast_dtype("cuda") if autocast else conv.weight.dtype
+    if (self.custom_stem and (autocast or torch.backends.cudnn.allow_tf32)
+        and tuple(frames.shape[1:]) == (84, 84, 4) and tuple(conv.weight.shape) == (32, 4, 8, 8)
+        and conv.weight.dtype == torch.float32 and dtype in (torch.float32, torch.bfloat16)):
+      hidden = _StemConvReLU.apply(frames, conv.weight, conv.bias, dtype)
     else:
-      hidden = torch.relu(nn.functional.conv2d(s2d, weight, bias))
+      s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0).permute(0, 3, 1, 2)
+      weight, bias = self._s2d_weight(conv), conv.bias
+      if self.fused_conv_relu:
+        if s2d.dtype != weight.dtype:
+          weight, bias = weight.to(s2d.dtype), bias.to(s2d.dtype)
+        hidden = _ConvBiasReLU.apply(s2d, weight, bias, (1, 1), (0, 0))
+      else:
+        hidden = torch.relu(nn.functional.conv2d(s2d, weight, bias))
     layers = list(self.children())[2:]          # after conv-0, relu-0
     while len(layers) >= 2 and isinstance(layers[0], nn.Conv2d) and isinstance(layers[1], nn.ReLU):
       hidden = self._conv_relu(hidden, layers[0])

@@ -202,6 +202,17 @@ int derl_b200_frames_to_s2d(const uint8_t* src_dev, int64_t batch, int64_t heigh
                             int64_t width, int64_t channels, int64_t block, void* dst_dev,
                             int dst_dtype, double divisor, void* stream);
 
+/* ------------------------------------------------------------------ K6: stem conv on uint8 frames
+ * The reference's first layer (derl/models.py:102-103,117-123): permute, `.float()/255`,
+ * nn.Conv2d(4, 32, 8, 4), nn.ReLU — evaluated straight from the uint8 frames on the tensor
+ * cores (bf16 MMA with the weights split hi + lo, fp32 accumulate), without materialising a
+ * floating-point copy of the frames.  Fixed to the Atari stem geometry:
+ *   frames [batch, 84, 84, 4] uint8 NHWC; weight [32, 4, 8, 8] float32 (conv layout); bias [32];
+ *   out [batch, 20, 20, 32] channels-last, DERL_DTYPE_F32 or DERL_DTYPE_BF16.
+ */
+int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const float* weight_dev,
+                             const float* bias_dev, void* out_dev, int out_dtype, void* stream);
+
 /* ------------------------------------------------------------------ K5: ReLU backward + bias grad
  * One pass over a channels-last activation gradient [rows, channels] (rows = B*H*W):
  *     grad_pre = out > 0 ? grad_out : 0;   bias_grad[c] = sum over rows of grad_pre[:, c]

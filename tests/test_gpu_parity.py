@@ -646,6 +646,48 @@ def test_relu_backward_bias_kernel_vs_aten(dtype):
     K.relu_bwd_bias(torch.zeros(2, 8, 3, 3, device=DEV), torch.zeros(2, 8, 3, 3, device=DEV))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv_kernel_vs_float32_convolution(dtype):
+  """K6: conv 8x8/4 + bias + ReLU straight from uint8 frames (bf16 MMA, weights hi + lo) against
+  the reference formulation in float32 (`.float()/255` -> conv2d -> relu, TF32 off).  The
+  split keeps ~16 weight bits: 1e-4 relative on activations of O(1) (bf16 output: bf16 rounding)."""
+  torch.backends.cudnn.allow_tf32 = False
+  gen = torch.Generator(device=DEV).manual_seed(12)
+  weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.1
+  bias = torch.randn(32, device=DEV, generator=gen) * 0.1
+  for batch in (1, 2, 3, 301):
+    frames = torch.randint(0, 256, (batch, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
+    out = K.stem_conv_relu(frames, weight, bias, dtype)
+    want = torch.relu(torch.nn.functional.conv2d(frames.permute(0, 3, 1, 2).float() / 255, weight,
+                                                 bias, stride=4)).permute(0, 2, 3, 1)
+    assert out.shape == (batch, 20, 20, 32) and out.dtype == dtype
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert torch.allclose(out.float(), want, rtol=tol, atol=tol * float(want.abs().max())), \
+        (out.float() - want).abs().max()
+    assert (out.float() - want).abs().max() <= tol * want.abs().max()
+  torch.backends.cudnn.allow_tf32 = True
+
+
+def test_stem_autograd_matches_cudnn_path():
+  """NatureCNN with the K6 stem (TF32 allowed) vs the cuDNN stem: outputs and all parameter
+  gradients agree to TF32-level tolerance; the stem weight gradient lands in [32,4,8,8] layout."""
+  torch.manual_seed(0)
+  model = d.NatureCNNModel([4, 1])
+  frames = torch.randint(0, 256, (64, 84, 84, 4), dtype=torch.uint8, device=DEV)
+  res = {}
+  for custom in (True, False):
+    d.NatureCNNBase.custom_stem = custom
+    model.zero_grad()
+    logits, values = model(frames)
+    (logits.square().sum() + values.sum()).backward()
+    res[custom] = (logits.detach().clone(), [p.grad.clone() for p in model.parameters()])
+  d.NatureCNNBase.custom_stem = True
+  assert torch.allclose(res[True][0], res[False][0], rtol=2e-2, atol=2e-3)
+  for a, b in zip(res[True][1], res[False][1]):
+    assert a.shape == b.shape
+    assert (a - b).abs().max() <= 2e-2 * b.abs().max() + 1e-6
+
+
 def test_space_to_depth_first_conv_equals_plain_formulation():
   """NatureCNNBase runs the 8x8/4 stem as a 2x2/1 conv on the space-to-depth tensor with
   re-indexed weights (derl_b200/models.py): same parameters, same function as the
