@@ -19,6 +19,7 @@
 //     reference's input scaling is applied to the fp32 accumulator in the epilogue;
 //   * epilogue: acc/255 + bias, ReLU, full-sector stores of the channels-last activation.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -196,9 +197,198 @@ stem_conv_relu_kernel(const uint8_t* __restrict__ frames, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ integer tensor-core variant
+// sm_100a still has INT8 tensor cores (removed on sm_103): the frames ARE uint8, so the MMA can
+// consume them raw — no float conversion of the frame at all — if the weights are expressed as
+// signed 8-bit digits.  Per output channel n: scale s = max|W[:, n]| / 127,
+//   W ~= s * (q1 + q2 / 254),  q1 = round(W / s),  q2 = round((W - s*q1) * 254 / s),
+// residual <= s / 508 (1.6e-5 of the channel's largest weight: below TF32's 2^-11 per product).
+// mma.sync m16n8k32 u8 x s8 -> s32 accumulates both digit planes EXACTLY (|acc| < 2^24); the
+// epilogue recombines them in fp32: y = relu((acc1 * s + acc2 * s / 254) / 255 + bias).
+// One k32 step is one 32-byte tap row in natural order; a CTA of 9 warps takes one frame per
+// iteration (3 m16 tiles per warp), raw frames double-buffered by TMA bulk copies.
+constexpr int kI8Warps = 9, kI8Threads = kI8Warps * 32, kI8Tiles = 3, kPlanes = 2;
+
+struct StemI8Smem {
+  static constexpr size_t raw_off = 0;                                  // [2][28224] u8
+  static constexpr size_t w_off = raw_off + 2 * (size_t)kImgBytes;      // [8][4][32] uint4
+  static constexpr size_t scale_off = w_off + 8 * 4 * 32 * 16;          // [32] float s
+  static constexpr size_t bias_off = scale_off + kOutC * 4;
+  static constexpr size_t bar_off = bias_off + kOutC * 4;
+  static constexpr size_t bytes = bar_off + 16;
+};
+
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], const unsigned (&a)[4], unsigned b0,
+                                         unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kI8Threads)
+stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ weight,
+                         const float* __restrict__ bias, OT* __restrict__ out, long long batch) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint4* wsm = reinterpret_cast<uint4*>(smem + StemI8Smem::w_off);
+  float* ssm = reinterpret_cast<float*>(smem + StemI8Smem::scale_off);
+  float* bsm = reinterpret_cast<float*>(smem + StemI8Smem::bias_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + StemI8Smem::bar_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const long long first = blockIdx.x, stride = gridDim.x;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+    for (int b = 0; b < 2; ++b) {
+      if (first + b * stride < batch) {
+        mbar_expect_tx(&full[b], kImgBytes);
+        bulk_g2s(smem + StemI8Smem::raw_off + (size_t)b * kImgBytes,
+                 frames + (first + b * stride) * kImgBytes, kImgBytes, &full[b]);
+      }
+    }
+  }
+  // ---- per-channel scales: warp w reduces channels w, w+9, ...
+  for (int n = warp; n < kOutC; n += kI8Warps) {
+    float m = 0.f;
+    for (int k = lane; k < kTaps; k += 32) m = fmaxf(m, fabsf(__ldg(weight + n * kTaps + k)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) ssm[n] = m > 0.f ? m / 127.f : 1.f;
+  }
+  if (tid < kOutC) bsm[tid] = __ldg(bias + tid);
+  __syncthreads();
+  // ---- digit planes as B fragments: wsm[kh][nt][lane] = {p1 b0, p1 b1, p2 b0, p2 b1}
+  for (int e = tid; e < 8 * 4 * 32; e += kI8Threads) {
+    const int ln = e & 31, nt = (e >> 5) & 3, kh = e >> 7;
+    const int tt = ln & 3, n = nt * 8 + (ln >> 2);
+    const float s = ssm[n], inv = 1.f / s;
+    unsigned words[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int kw = half * 4 + tt;                 // tap-row bytes 16*half + 4*tt + c
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float w = __ldg(weight + ((n * kImgC + c) * 8 + kh) * 8 + kw);
+        const float q1 = rintf(w * inv);
+        const float q2 = fminf(fmaxf(rintf((w - q1 * s) * 254.f * inv), -127.f), 127.f);
+        words[half] |= ((unsigned)(int)q1 & 0xffu) << (8 * c);
+        words[2 + half] |= ((unsigned)(int)q2 & 0xffu) << (8 * c);
+      }
+    }
+    wsm[e] = make_uint4(words[0], words[1], words[2], words[3]);
+  }
+  __syncthreads();
+
+  // byte offsets (raw frame, tap row 0) of this lane's rows; tiles beyond 24 are masked
+  int base0[kI8Tiles], base1[kI8Tiles];
+  bool live[kI8Tiles];
+#pragma unroll
+  for (int m = 0; m < kI8Tiles; ++m) {
+    const int tile = warp * kI8Tiles + m;
+    live[m] = tile < kPix / 16;
+    const int p0 = (live[m] ? tile : 0) * 16 + g, p1 = p0 + 8;
+    base0[m] = (p0 / kOutHW) * 4 * (kImgW * kImgC) + (p0 % kOutHW) * 16 + 4 * t;
+    base1[m] = (p1 / kOutHW) * 4 * (kImgW * kImgC) + (p1 % kOutHW) * 16 + 4 * t;
+  }
+
+  int it = 0;
+  for (long long f = first; f < batch; f += stride, ++it) {
+    const int buf = it & 1;
+    const uint8_t* raw = smem + StemI8Smem::raw_off + (size_t)buf * kImgBytes;
+    mbar_wait(&full[buf], (unsigned)((it >> 1) & 1));
+
+    int acc[kI8Tiles][4][kPlanes][4];
+#pragma unroll
+    for (int m = 0; m < kI8Tiles; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int p = 0; p < kPlanes; ++p)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[m][n][p][k] = 0;
+
+#pragma unroll 2
+    for (int kh = 0; kh < 8; ++kh) {
+      uint4 bq[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) bq[n] = wsm[(kh * 4 + n) * 32 + lane];
+      const int koff = kh * (kImgW * kImgC);
+#pragma unroll
+      for (int m = 0; m < kI8Tiles; ++m) {
+        if (!live[m]) continue;  // warp-uniform
+        const unsigned a[4] = {*reinterpret_cast<const unsigned*>(raw + base0[m] + koff),
+                               *reinterpret_cast<const unsigned*>(raw + base1[m] + koff),
+                               *reinterpret_cast<const unsigned*>(raw + base0[m] + koff + 16),
+                               *reinterpret_cast<const unsigned*>(raw + base1[m] + koff + 16)};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          mma_u8s8(acc[m][n][0], a, bq[n].x, bq[n].y);
+          mma_u8s8(acc[m][n][1], a, bq[n].z, bq[n].w);
+        }
+      }
+    }
+    __syncthreads();  // all warps are done with raw[buf]: refill it with the frame after next
+    if (tid == 0 && f + 2 * stride < batch) {
+      mbar_expect_tx(&full[buf], kImgBytes);
+      bulk_g2s(smem + StemI8Smem::raw_off + (size_t)buf * kImgBytes,
+               frames + (f + 2 * stride) * kImgBytes, kImgBytes, &full[buf]);
+    }
+
+    OT* dst = out + f * (long long)(kPix * kOutC);
+    const float inv255 = 1.0f / 255.0f, inv254 = 1.0f / 254.0f;
+#pragma unroll
+    for (int m = 0; m < kI8Tiles; ++m) {
+      if (!live[m]) continue;
+      const int p0 = (warp * kI8Tiles + m) * 16 + g;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int ch = n * 8 + 2 * t;
+        const float s0 = ssm[ch] * inv255, s1 = ssm[ch + 1] * inv255;
+        const float b0 = bsm[ch], b1 = bsm[ch + 1];
+        float y[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sc = (k & 1) ? s1 : s0;
+          y[k] = ((float)acc[m][n][0][k] + (float)acc[m][n][1][k] * inv254) * sc +
+                 ((k & 1) ? b1 : b0);
+          y[k] = fmaxf(y[k], 0.f);
+        }
+        store2<OT>(dst + p0 * kOutC + ch, y[0], y[1]);
+        store2<OT>(dst + (p0 + 8) * kOutC + ch, y[2], y[3]);
+      }
+    }
+  }
+}
+
+template <typename OT>
+int launch_i8(const uint8_t* frames, const float* weight, const float* bias, void* out,
+              long long batch, cudaStream_t st) {
+  auto kern = stem_conv_relu_i8_kernel<OT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DERL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)StemI8Smem::bytes));
+    attr_set = true;
+  }
+  long long grid = batch;
+  const long long cap = (long long)sm_count() * 3;   // 3 CTAs of ~72 KB smem per SM
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, kI8Threads, StemI8Smem::bytes, st>>>(frames, weight, bias,
+                                                              reinterpret_cast<OT*>(out), batch);
+  DERL_LAUNCH_CHECK("stem_conv_relu_i8_kernel");
+  return DERL_OK;
+}
+
 template <typename OT>
 int launch(const uint8_t* frames, const float* weight, const float* bias, void* out,
            long long batch, cudaStream_t st) {
+  static const char* variant = getenv("DERL_STEM_VARIANT");  // tuning knob: "bf16" | "i8"
+  if (variant == nullptr || variant[0] == 'i') return launch_i8<OT>(frames, weight, bias, out, batch, st);
   auto kern = stem_conv_relu_kernel<OT>;
   static bool attr_set = false;
   if (!attr_set) {
