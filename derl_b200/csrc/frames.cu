@@ -131,6 +131,35 @@ frames_to_s2d_staged_kernel(const uint4* __restrict__ src, OT* __restrict__ dst,
   }
 }
 
+// Space-to-depth / depth-to-space of a channels-last activation, 16 bytes per thread:
+//   s2d[b, Y, X, (i*s + j)*C + c] = x[b, s*Y + i, s*X + j, c]      (inverse: roles swapped)
+// Runs of s*C elements are contiguous on both sides.  Used (with its inverse as backward) to
+// feed a strided conv whose kernel is 2 x stride as a 2x2 / stride-1 conv.
+template <bool kInverse>
+__global__ void __launch_bounds__(256)
+space_to_depth_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total,
+                      int hy, int wx, int s, int cq) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int run = s * cq;  // 16-byte units per contiguous (j, c) run
+  for (long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x; d < total; d += stride) {
+    // d indexes the space-to-depth tensor: ((((b*hy + Y)*wx + X)*s + i)*run + r)
+    const long long q = d / run;
+    const int r = (int)(d - q * run);
+    const long long q2 = q / s;
+    const int i = (int)(q - q2 * s);
+    const long long q3 = q2 / wx;                 // b*hy + Y
+    const int X = (int)(q2 - q3 * wx);
+    const long long b = q3 / hy;
+    const int Y = (int)(q3 - b * hy);
+    const long long x = (((b * hy + Y) * s + i) * (long long)wx + X) * run + r;  // plain layout
+    if (kInverse) {
+      dst[x] = __ldg(src + d);
+    } else {
+      dst[d] = __ldg(src + x);
+    }
+  }
+}
+
 template <typename OT>
 int launch(const void* src, void* dst, long long granules, int wx, int s, float divisor,
            cudaStream_t st) {
@@ -172,6 +201,41 @@ int launch(const void* src, void* dst, long long granules, int wx, int s, float 
 }  // namespace derl
 
 using namespace derl;
+
+extern "C" int derl_b200_space_to_depth(const void* src, int64_t batch, int64_t height,
+                                        int64_t width, int64_t channel_bytes, int64_t block,
+                                        int inverse, void* dst, void* stream) {
+  DERL_REQUIRE(src && dst && batch >= 0, "space_to_depth: bad arguments");
+  DERL_REQUIRE(block >= 1 && height % block == 0 && width % block == 0 && height >= block &&
+                   width >= block,
+               "space_to_depth: height=%lld, width=%lld must be multiples of block=%lld",
+               (long long)height, (long long)width, (long long)block);
+  DERL_REQUIRE(channel_bytes >= 16 && channel_bytes % 16 == 0,
+               "space_to_depth: channel bytes (%lld) must be a multiple of 16",
+               (long long)channel_bytes);
+  DERL_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
+               "space_to_depth: src and dst must be 16-byte aligned");
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  const long long total = batch * height * width * (channel_bytes / 16);
+  if (total == 0) return DERL_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 64;
+  if (blocks > cap) blocks = cap;
+  const int hy = (int)(height / block), wx = (int)(width / block), cq = (int)(channel_bytes / 16);
+  cudaStream_t st = as_stream(stream);
+  if (inverse) {
+    space_to_depth_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), total, hy, wx,
+        (int)block, cq);
+  } else {
+    space_to_depth_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), total, hy, wx,
+        (int)block, cq);
+  }
+  DERL_LAUNCH_CHECK("space_to_depth_kernel");
+  return DERL_OK;
+}
 
 extern "C" int derl_b200_frames_to_s2d(const uint8_t* src, int64_t batch, int64_t height,
                                        int64_t width, int64_t channels, int64_t block,

@@ -178,9 +178,14 @@ class NatureCNNBase(nn.Sequential):
     if (self.space_to_depth and self.space_to_depth_hidden and hidden.is_cuda
         and self._s2d_ok(conv, *hidden.shape[2:])):
       s, (batch, chans, height, width) = stride[0], hidden.shape
-      blocks = hidden.permute(0, 2, 3, 1).reshape(batch, height // s, s, width // s, s, chans)
-      hidden = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s,
-                                                        s * s * chans).permute(0, 3, 1, 2)
+      nhwc = hidden.permute(0, 2, 3, 1)   # a view: channels-last storage is NHWC-contiguous
+      if nhwc.is_contiguous() and (chans * hidden.element_size()) % 16 == 0:
+        from . import ops  # noqa: F401
+        hidden = torch.ops.derl_b200.space_to_depth(nhwc, s, False).permute(0, 3, 1, 2)
+      else:
+        blocks = nhwc.reshape(batch, height // s, s, width // s, s, chans)
+        hidden = blocks.permute(0, 1, 3, 2, 4, 5).reshape(batch, height // s, width // s,
+                                                          s * s * chans).permute(0, 3, 1, 2)
       weight, stride = self._s2d_weight(conv), (1, 1)
     if (self.fused_conv_relu and hidden.is_cuda and bias is not None and conv.groups == 1
         and conv.dilation == (1, 1) and isinstance(conv.padding, tuple)):

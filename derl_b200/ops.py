@@ -294,6 +294,49 @@ def _(frames, block, dtype, divisor):
                           dtype=dtype)
 
 
+@torch.library.custom_op("derl_b200::space_to_depth", mutates_args=(), device_types="cuda")
+def space_to_depth(x: Tensor, block: int, inverse: bool = False) -> Tensor:
+  """NHWC-contiguous [B,H,W,C] -> [B,H/block,W/block,block*block*C] (inverse: the other way)."""
+  _dense(x, "x")
+  _need(x.dim() == 4, f"expected [B, H, W, C], got {tuple(x.shape)}")
+  batch, height, width, chans = x.shape
+  if inverse:
+    _need(chans % (block * block) == 0, "channels must be divisible by block^2")
+    chans //= block * block
+    height, width = height * block, width * block
+  _need(height % block == 0 and width % block == 0 and (chans * x.element_size()) % 16 == 0,
+        f"space_to_depth: unsupported shape {tuple(x.shape)} for block {block}")
+  shape = (batch, height, width, chans) if inverse else \
+      (batch, height // block, width // block, block * block * chans)
+  out = x.new_empty(shape)
+  with _device_of(x, "space_to_depth"):
+    _lib.check(_lib.load().derl_b200_space_to_depth(_p(x), batch, height, width,
+                                                    chans * x.element_size(), block,
+                                                    int(inverse), _p(out), _stream(x)),
+               "space_to_depth")
+  return out
+
+
+@space_to_depth.register_fake
+def _(x, block, inverse=False):
+  batch, height, width, chans = x.shape
+  if inverse:
+    return x.new_empty((batch, height * block, width * block, chans // (block * block)))
+  return x.new_empty((batch, height // block, width // block, block * block * chans))
+
+
+def _s2d_setup(ctx, inputs, output):
+  ctx.block, ctx.inverse = inputs[1], inputs[2]
+
+
+def _s2d_backward(ctx, grad):
+  return torch.ops.derl_b200.space_to_depth(grad.contiguous(), ctx.block, not ctx.inverse), \
+      None, None
+
+
+space_to_depth.register_autograd(_s2d_backward, setup_context=_s2d_setup)
+
+
 # --------------------------------------------------------------------------- K6: stem conv
 @torch.library.custom_op("derl_b200::stem_conv_relu", mutates_args=(), device_types="cuda")
 def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dtype) -> Tensor:

@@ -202,6 +202,15 @@ int derl_b200_frames_to_s2d(const uint8_t* src_dev, int64_t batch, int64_t heigh
                             int64_t width, int64_t channels, int64_t block, void* dst_dev,
                             int dst_dtype, double divisor, void* stream);
 
+/* Space-to-depth (inverse != 0: depth-to-space) of a channels-last activation
+ * [batch, height, width, C] with channel_bytes = C * sizeof(element), a multiple of 16:
+ *     s2d[b, Y, X, (i*block + j)*C + c] = x[b, block*Y + i, block*X + j, c]
+ * Lets a strided conv with kernel = 2 x stride (the reference's nn.Conv2d(32, 64, 4, 2),
+ * derl/models.py:104) run as a 2x2 / stride-1 conv; the inverse is its backward. */
+int derl_b200_space_to_depth(const void* src_dev, int64_t batch, int64_t height, int64_t width,
+                             int64_t channel_bytes, int64_t block, int inverse, void* dst_dev,
+                             void* stream);
+
 /* ------------------------------------------------------------------ K6: stem conv on uint8 frames
  * The reference's first layer (derl/models.py:102-103,117-123): permute, `.float()/255`,
  * nn.Conv2d(4, 32, 8, 4), nn.ReLU — evaluated straight from the uint8 frames on the tensor

@@ -647,6 +647,22 @@ def test_relu_backward_bias_kernel_vs_aten(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_space_to_depth_kernel_and_its_inverse(dtype):
+  gen = torch.Generator(device=DEV).manual_seed(3)
+  for shape, block in (((5, 20, 20, 32), 2), ((3, 8, 12, 8), 4), ((2, 6, 6, 64), 3)):
+    x = torch.randn(shape, device=DEV, generator=gen).to(dtype).requires_grad_()
+    batch, height, width, chans = shape
+    want = x.detach().reshape(batch, height // block, block, width // block, block, chans) \
+        .permute(0, 1, 3, 2, 4, 5).reshape(batch, height // block, width // block, -1)
+    got = K.space_to_depth(x, block, False)
+    assert torch.equal(got, want)
+    assert torch.equal(K.space_to_depth(got.detach(), block, True), x.detach())
+    grad = torch.randn_like(got)
+    got.backward(grad)
+    assert torch.equal(x.grad, K.space_to_depth(grad, block, True))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stem_conv_kernel_vs_float32_convolution(dtype):
   """K6: conv 8x8/4 + bias + ReLU straight from uint8 frames (bf16 MMA, weights hi + lo) against
   the reference formulation in float32 (`.float()/255` -> conv2d -> relu, TF32 off).  The
