@@ -56,8 +56,8 @@ def parse_args():
                  help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
   p.add_argument("--cpu-envs", type=int, default=32,
                  help="envs of the bounded CPU-baseline sample (same horizon/epochs/minibatches)")
-  p.add_argument("--s2d-hidden", action="store_true",
-                 help="A/B switch: evaluate the 4x4/2 conv in space-to-depth form as well")
+  p.add_argument("--no-s2d-hidden", action="store_true",
+                 help="A/B switch: keep the 4x4/2 conv strided (cuDNN strided dgrad)")
   p.add_argument("--torch-profile", default=None,
                  help="diagnostic: write a torch.profiler kernel table of one extra step here")
   p.add_argument("--no-e2e", action="store_true")
@@ -364,8 +364,8 @@ def run_ours(args, rank, world, local):
   torch.backends.cudnn.allow_tf32 = tf32
   torch.backends.cuda.matmul.allow_tf32 = tf32
 
-  if args.s2d_hidden:
-    d.NatureCNNBase.space_to_depth_hidden = True
+  if args.no_s2d_hidden:
+    d.NatureCNNBase.space_to_depth_hidden = False
   torch.manual_seed(0)  # identical initial weights on every rank
   model = d.NatureCNNModel([args.nactions, 1])
   if args.net == "bf16":

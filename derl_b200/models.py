@@ -97,16 +97,17 @@ class _ConvBiasReLU(torch.autograd.Function):
 
 
 class _StemConvReLU(torch.autograd.Function):
-  """The 8x8/4 stem + bias + ReLU straight from uint8 frames (derl_b200 K6) forward; backward =
-  K5 (ReLU mask + bias gradient) and the weight gradient of the equivalent space-to-depth conv
-  (K4 re-creates the float frames only here, cuDNN wgrad), mapped back to [32, 4, 8, 8]."""
+  """The 8x8/4 stem + bias + ReLU straight from uint8 frames (derl_b200 K6) forward, optionally
+  emitting the space-to-depth(2) arrangement the next layer consumes; backward = K5 (ReLU mask +
+  bias gradient) and the weight gradient of the equivalent space-to-depth conv (K4 re-creates
+  the float frames only here, cuDNN wgrad), mapped back to [32, 4, 8, 8]."""
 
   @staticmethod
-  def forward(ctx, frames, weight, bias, dtype):
-    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype)
+  def forward(ctx, frames, weight, bias, dtype, out_block):
+    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype, out_block)
     out = out.permute(0, 3, 1, 2)   # channels-last storage seen as NCHW
     ctx.save_for_backward(frames, out)
-    ctx.weight_dtype = weight.dtype
+    ctx.weight_dtype, ctx.out_block = weight.dtype, out_block
     return out
 
   @staticmethod
@@ -114,6 +115,10 @@ class _StemConvReLU(torch.autograd.Function):
     frames, out = ctx.saved_tensors
     grad_out = grad_out.contiguous(memory_format=torch.channels_last)
     grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out)
+    if ctx.out_block == 2:          # [B,128,10,10] (i, j, c) channels -> [B,32,20,20]
+      grad_b = grad_b.view(4, 32).sum(0)
+      grad_pre = torch.ops.derl_b200.space_to_depth(grad_pre.permute(0, 2, 3, 1), 2, True)
+      grad_pre = grad_pre.permute(0, 3, 1, 2)
     s2d = torch.ops.derl_b200.frames_to_s2d(frames, 4, out.dtype, 255.0).permute(0, 3, 1, 2)
     shape_only = s2d.new_empty((32, 64, 2, 2)).contiguous(memory_format=torch.channels_last)
     _, grad_w2, _ = torch.ops.aten.convolution_backward(
@@ -121,7 +126,7 @@ class _StemConvReLU(torch.autograd.Function):
         [False, True, False])
     # [O, (i, j, c), a, b] -> [O, c, 4a + i, 4b + j]
     grad_w = grad_w2.reshape(32, 4, 4, 4, 2, 2).permute(0, 3, 4, 1, 5, 2).reshape(32, 4, 8, 8)
-    return None, grad_w.to(ctx.weight_dtype), grad_b, None
+    return None, grad_w.to(ctx.weight_dtype), grad_b, None, None
 
 
 def _conv_out(size, conv):
@@ -149,8 +154,8 @@ class NatureCNNBase(nn.Sequential):
   custom_stem = True             # K6: stem conv straight from uint8 frames (needs TF32 allowed
                                  # or autocast: it is a reduced-precision tensor-core path)
   space_to_depth = True          # class-wide switches (tests compare the formulations)
-  space_to_depth_hidden = False  # ... also for strided convs after the stem: measured 3 % SLOWER
-                                 # on B200 (two permute copies outweigh cuDNN's strided dgrad)
+  space_to_depth_hidden = True   # ... also for strided convs after the stem (the 4x4/2 layer):
+                                 # avoids cuDNN's strided dgrad + layout folds (-5 % per update)
   fused_conv_relu = True
 
   @staticmethod
@@ -169,14 +174,18 @@ class NatureCNNBase(nn.Sequential):
             and conv.padding == (0, 0) and conv.dilation == (1, 1) and conv.groups == 1
             and height % s == 0 and width % s == 0)
 
-  def _conv_relu(self, hidden, conv):
+  def _conv_relu(self, hidden, conv, pre_s2d=False):
     """conv + bias + ReLU.  A strided conv with kernel = 2 x stride is evaluated as a 2x2 /
     stride-1 conv over the space-to-depth activation (same parameters, same sums): cuDNN's
-    strided dgrad for the 4x4/2 layer alone was 34 % of the update, the stride-1 form runs
-    on its fast implicit-GEMM kernels.  On the GPU conv, bias and ReLU are one cuDNN call."""
+    strided dgrad + its layout folds for the 4x4/2 layer were 14 % of the update in situ, the
+    stride-1 form runs on plain implicit-GEMM kernels and the re-arrangement is one
+    derl_b200.space_to_depth pass (or free when the stem kernel already emitted that layout:
+    `pre_s2d`).  On the GPU conv, bias and ReLU are one cuDNN call."""
     weight, bias, stride = conv.weight, conv.bias, conv.stride
-    if (self.space_to_depth and self.space_to_depth_hidden and hidden.is_cuda
-        and self._s2d_ok(conv, *hidden.shape[2:])):
+    if pre_s2d:
+      weight, stride = self._s2d_weight(conv), (1, 1)
+    elif (self.space_to_depth and self.space_to_depth_hidden and hidden.is_cuda
+          and self._s2d_ok(conv, *hidden.shape[2:])):
       s, (batch, chans, height, width) = stride[0], hidden.shape
       nhwc = hidden.permute(0, 2, 3, 1)   # a view: channels-last storage is NHWC-contiguous
       if nhwc.is_contiguous() and (chans * hidden.element_size()) % 16 == 0:
@@ -205,10 +214,14 @@ class NatureCNNBase(nn.Sequential):
     from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
     autocast = torch.is_autocast_enabled("cuda")
     dtype = torch.get_autocast_dtype("cuda") if autocast else conv.weight.dtype
+    pre_s2d = False
     if (self.custom_stem and (autocast or torch.backends.cudnn.allow_tf32)
         and tuple(frames.shape[1:]) == (84, 84, 4) and tuple(conv.weight.shape) == (32, 4, 8, 8)
         and conv.weight.dtype == torch.float32 and dtype in (torch.float32, torch.bfloat16)):
-      hidden = _StemConvReLU.apply(frames, conv.weight, conv.bias, dtype)
+      nxt = list(self.children())[2]
+      pre_s2d = (self.space_to_depth and self.space_to_depth_hidden and isinstance(nxt, nn.Conv2d)
+                 and nxt.stride == (2, 2) and self._s2d_ok(nxt, 20, 20))
+      hidden = _StemConvReLU.apply(frames, conv.weight, conv.bias, dtype, 2 if pre_s2d else 1)
     else:
       s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0).permute(0, 3, 1, 2)
       weight, bias = self._s2d_weight(conv), conv.bias
@@ -220,7 +233,8 @@ class NatureCNNBase(nn.Sequential):
         hidden = torch.relu(nn.functional.conv2d(s2d, weight, bias))
     layers = list(self.children())[2:]          # after conv-0, relu-0
     while len(layers) >= 2 and isinstance(layers[0], nn.Conv2d) and isinstance(layers[1], nn.ReLU):
-      hidden = self._conv_relu(hidden, layers[0])
+      hidden = self._conv_relu(hidden, layers[0], pre_s2d)
+      pre_s2d = False
       layers = layers[2:]
     if (len(layers) == 2 and isinstance(layers[0], nn.Flatten) and isinstance(layers[1], nn.Linear)
         and hidden.is_contiguous(memory_format=torch.channels_last)):

@@ -339,9 +339,11 @@ space_to_depth.register_autograd(_s2d_backward, setup_context=_s2d_setup)
 
 # --------------------------------------------------------------------------- K6: stem conv
 @torch.library.custom_op("derl_b200::stem_conv_relu", mutates_args=(), device_types="cuda")
-def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dtype) -> Tensor:
+def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dtype,
+                   out_block: int = 1) -> Tensor:
   """relu(conv2d(frames/255, weight, bias, stride 4)) for uint8 NHWC frames [B,84,84,4] and the
-  Atari stem weight [32,4,8,8]; returns the channels-last activation [B,20,20,32]."""
+  Atari stem weight [32,4,8,8]; returns the channels-last activation [B,20,20,32], or its
+  space-to-depth(2) arrangement [B,10,10,128] when out_block == 2."""
   _dense(frames, "frames", (torch.uint8,))
   _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
   _dense(weight, "weight", (torch.float32,))
@@ -349,17 +351,20 @@ def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dt
   _need(tuple(weight.shape) == (32, 4, 8, 8) and tuple(bias.shape) == (32,),
         "stem_conv_relu is specialised to weight [32,4,8,8], bias [32]")
   _need(dtype in (torch.float32, torch.bfloat16), "dtype must be float32 or bfloat16")
-  out = torch.empty((frames.shape[0], 20, 20, 32), dtype=dtype, device=frames.device)
+  _need(out_block in (1, 2), "out_block must be 1 or 2")
+  shape = (frames.shape[0], 20, 20, 32) if out_block == 1 else (frames.shape[0], 10, 10, 128)
+  out = torch.empty(shape, dtype=dtype, device=frames.device)
   with _device_of(frames, "stem_conv_relu"):
     _lib.check(_lib.load().derl_b200_stem_conv_relu(_p(frames), frames.shape[0], _p(weight),
                                                     _p(bias), _p(out), _S2D_DTYPES[dtype],
-                                                    _stream(frames)), "stem_conv_relu")
+                                                    out_block, _stream(frames)), "stem_conv_relu")
   return out
 
 
 @stem_conv_relu.register_fake
-def _(frames, weight, bias, dtype):
-  return frames.new_empty((frames.shape[0], 20, 20, 32), dtype=dtype)
+def _(frames, weight, bias, dtype, out_block=1):
+  shape = (frames.shape[0], 20, 20, 32) if out_block == 1 else (frames.shape[0], 10, 10, 128)
+  return frames.new_empty(shape, dtype=dtype)
 
 
 # --------------------------------------------------------------------------- K5: ReLU bwd

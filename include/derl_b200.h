@@ -213,14 +213,19 @@ int derl_b200_space_to_depth(const void* src_dev, int64_t batch, int64_t height,
 
 /* ------------------------------------------------------------------ K6: stem conv on uint8 frames
  * The reference's first layer (derl/models.py:102-103,117-123): permute, `.float()/255`,
- * nn.Conv2d(4, 32, 8, 4), nn.ReLU — evaluated straight from the uint8 frames on the tensor
- * cores (bf16 MMA with the weights split hi + lo, fp32 accumulate), without materialising a
- * floating-point copy of the frames.  Fixed to the Atari stem geometry:
+ * nn.Conv2d(4, 32, 8, 4), nn.ReLU — evaluated straight from the uint8 frames on the INT8
+ * tensor cores of sm_100a (raw frame bytes x two signed 8-bit digit planes of the weights,
+ * exact int32 accumulation, fp32 recombination), without materialising a floating-point copy
+ * of the frames.  Fixed to the Atari stem geometry:
  *   frames [batch, 84, 84, 4] uint8 NHWC; weight [32, 4, 8, 8] float32 (conv layout); bias [32];
- *   out [batch, 20, 20, 32] channels-last, DERL_DTYPE_F32 or DERL_DTYPE_BF16.
+ *   out_block 1: out [batch, 20, 20, 32] channels-last;
+ *   out_block 2: out [batch, 10, 10, 128], the space-to-depth(2) arrangement of the same
+ *                activation (what derl_b200_space_to_depth would produce from it);
+ *   out_dtype DERL_DTYPE_F32 or DERL_DTYPE_BF16.
  */
 int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const float* weight_dev,
-                             const float* bias_dev, void* out_dev, int out_dtype, void* stream);
+                             const float* bias_dev, void* out_dev, int out_dtype, int out_block,
+                             void* stream);
 
 /* ------------------------------------------------------------------ K5: ReLU backward + bias grad
  * One pass over a channels-last activation gradient [rows, channels] (rows = B*H*W):

@@ -673,10 +673,12 @@ def test_stem_conv_kernel_vs_float32_convolution(dtype):
   bias = torch.randn(32, device=DEV, generator=gen) * 0.1
   for batch in (1, 2, 3, 301):
     frames = torch.randint(0, 256, (batch, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
-    out = K.stem_conv_relu(frames, weight, bias, dtype)
+    out = K.stem_conv_relu(frames, weight, bias, dtype, 1)
     want = torch.relu(torch.nn.functional.conv2d(frames.permute(0, 3, 1, 2).float() / 255, weight,
                                                  bias, stride=4)).permute(0, 2, 3, 1)
     assert out.shape == (batch, 20, 20, 32) and out.dtype == dtype
+    blocked = K.stem_conv_relu(frames, weight, bias, dtype, 2)   # same values, s2d(2) layout
+    assert torch.equal(blocked, K.space_to_depth(out, 2, False))
     tol = 1e-4 if dtype == torch.float32 else 1e-2
     assert torch.allclose(out.float(), want, rtol=tol, atol=tol * float(want.abs().max())), \
         (out.float() - want).abs().max()
@@ -691,17 +693,19 @@ def test_stem_autograd_matches_cudnn_path():
   model = d.NatureCNNModel([4, 1])
   frames = torch.randint(0, 256, (64, 84, 84, 4), dtype=torch.uint8, device=DEV)
   res = {}
-  for custom in (True, False):
-    d.NatureCNNBase.custom_stem = custom
+  for custom, hidden in ((True, True), (True, False), (False, True)):
+    d.NatureCNNBase.custom_stem, d.NatureCNNBase.space_to_depth_hidden = custom, hidden
     model.zero_grad()
     logits, values = model(frames)
     (logits.square().sum() + values.sum()).backward()
-    res[custom] = (logits.detach().clone(), [p.grad.clone() for p in model.parameters()])
-  d.NatureCNNBase.custom_stem = True
-  assert torch.allclose(res[True][0], res[False][0], rtol=2e-2, atol=2e-3)
-  for a, b in zip(res[True][1], res[False][1]):
-    assert a.shape == b.shape
-    assert (a - b).abs().max() <= 2e-2 * b.abs().max() + 1e-6
+    res[custom, hidden] = (logits.detach().clone(), [p.grad.clone() for p in model.parameters()])
+  d.NatureCNNBase.custom_stem = d.NatureCNNBase.space_to_depth_hidden = True
+  base = res[False, True]
+  for key in ((True, True), (True, False)):
+    assert torch.allclose(res[key][0], base[0], rtol=2e-2, atol=2e-3), key
+    for a, b in zip(res[key][1], base[1]):
+      assert a.shape == b.shape
+      assert (a - b).abs().max() <= 2e-2 * b.abs().max() + 1e-6, key
 
 
 def test_space_to_depth_first_conv_equals_plain_formulation():
@@ -718,13 +722,13 @@ def test_space_to_depth_first_conv_equals_plain_formulation():
   for s2d, fused in ((True, True), (True, False), (False, False), ("hidden", True)):
     d.NatureCNNBase.space_to_depth, d.NatureCNNBase.fused_conv_relu = bool(s2d), fused
     d.NatureCNNBase.space_to_depth_hidden = s2d == "hidden"
-    model.zero_grad()
+    model.zero_grad()  # (TF32 is off here, so the K6 stem is not in play: cuDNN float32 stem)
     logits, values = model(frames)
     (logits.square().sum() + values.sum()).backward()
     outs[s2d, fused] = (logits.detach().clone(), values.detach().clone(),
                         [p.grad.clone() for p in model.parameters()])
   d.NatureCNNBase.space_to_depth = d.NatureCNNBase.fused_conv_relu = True
-  d.NatureCNNBase.space_to_depth_hidden = False
+  d.NatureCNNBase.space_to_depth_hidden = True
   torch.backends.cudnn.allow_tf32 = True
   plain = outs[False, False]
   for key in ((True, True), (True, False), ("hidden", True)):
