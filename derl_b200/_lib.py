@@ -44,7 +44,8 @@ SIGNATURES = {
                                            _ptr, _ptr, _size, _ptr]),
     "derl_b200_frames_to_s2d": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _f64, _ptr]),
     "derl_b200_relu_bwd_bias_workspace_bytes": (_size, [_i64]),
-    "derl_b200_relu_bwd_bias": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _ptr, _size, _ptr]),
+    "derl_b200_relu_bwd_bias": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _int, _i64, _i64,
+                                       _ptr, _size, _ptr]),
     "derl_b200_stem_conv_relu": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _ptr]),
     "derl_b200_space_to_depth": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,

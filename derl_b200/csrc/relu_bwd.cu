@@ -68,12 +68,16 @@ struct Vec4<__half> {
   }
 };
 
-// quads = C / 4 divides kThreads; thread t owns channel quad (t % quads) of rows t / quads + k * rpb
+// quads = C / 4 divides kThreads; thread t owns channel quad (t % quads) of rows t / quads + k * rpb.
+// unblock > 1: the inputs are a space-to-depth(unblock) arrangement [B, hy, wx, unblock^2 * c]
+// of an activation [B, hy*unblock, wx*unblock, c]; grad_pre is written in the PLAIN layout
+// (the depth-to-space pass is folded into the store addresses).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
                      T* __restrict__ grad_pre, float* __restrict__ bias_grad, long long rows,
-                     int quads, float* __restrict__ partials, unsigned* __restrict__ ticket) {
+                     int quads, float* __restrict__ partials, unsigned* __restrict__ ticket,
+                     int unblock, int hy, int wx) {
   using V = typename Vec4<T>::type;
   __shared__ float4 red[kThreads];
   __shared__ int is_last;
@@ -94,7 +98,17 @@ relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
       gv[k] = ov[k] > 0.f ? gv[k] : 0.f;
       acc[k] += gv[k];
     }
-    p[at] = Vec4<T>::pack(gv);
+    long long to = at;
+    if (unblock > 1) {
+      const int cq = quads / (unblock * unblock);       // quads per plain pixel
+      const int blk = quad / cq, c4 = quad - blk * cq;  // blk = i * unblock + j
+      const int i = blk / unblock, j = blk - i * unblock;
+      const long long by = r / wx;                      // b * hy + Y
+      const int X = (int)(r - by * wx);
+      const long long pixel = ((by * unblock + i) * wx + X) * unblock + j;
+      to = pixel * cq + c4;
+    }
+    p[to] = Vec4<T>::pack(gv);
   }
   red[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   __syncthreads();
@@ -130,7 +144,8 @@ relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
 
 template <typename T>
 int launch(const void* grad_out, const void* out, void* grad_pre, float* bias_grad,
-           long long rows, int channels, void* workspace, cudaStream_t st) {
+           long long rows, int channels, void* workspace, int unblock, int hy, int wx,
+           cudaStream_t st) {
   const int quads = channels / 4;
   const int rpb = kThreads / quads;
   long long blocks = (rows + rpb - 1) / rpb;
@@ -140,7 +155,7 @@ int launch(const void* grad_out, const void* out, void* grad_pre, float* bias_gr
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
   relu_bwd_bias_kernel<T><<<(unsigned)blocks, kThreads, 0, st>>>(
       reinterpret_cast<const T*>(grad_out), reinterpret_cast<const T*>(out),
-      reinterpret_cast<T*>(grad_pre), bias_grad, rows, quads, partials, ticket);
+      reinterpret_cast<T*>(grad_pre), bias_grad, rows, quads, partials, ticket, unblock, hy, wx);
   DERL_LAUNCH_CHECK("relu_bwd_bias_kernel");
   return DERL_OK;
 }
@@ -157,8 +172,20 @@ extern "C" size_t derl_b200_relu_bwd_bias_workspace_bytes(int64_t channels) {
 
 extern "C" int derl_b200_relu_bwd_bias(const void* grad_out, const void* out, void* grad_pre,
                                        float* bias_grad, int64_t rows, int64_t channels,
-                                       int dtype, void* workspace, size_t workspace_bytes,
-                                       void* stream) {
+                                       int dtype, int unblock, int64_t blocked_height,
+                                       int64_t blocked_width, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  DERL_REQUIRE(unblock >= 1, "relu_bwd_bias: unblock must be >= 1");
+  if (unblock > 1) {
+    DERL_REQUIRE(blocked_height >= 1 && blocked_width >= 1 &&
+                     rows % (blocked_height * blocked_width) == 0 &&
+                     channels % (4 * unblock * unblock) == 0,
+                 "relu_bwd_bias: rows=%lld / channels=%lld do not match a space-to-depth(%d) "
+                 "tensor of %lld x %lld blocks", (long long)rows, (long long)channels, unblock,
+                 (long long)blocked_height, (long long)blocked_width);
+    DERL_REQUIRE(grad_pre != grad_out && grad_pre != out,
+                 "relu_bwd_bias: the unblocking store cannot run in place");
+  }
   DERL_REQUIRE(grad_out && out && grad_pre && bias_grad && workspace,
                "relu_bwd_bias: null pointer");
   DERL_REQUIRE(rows >= 1, "relu_bwd_bias: rows must be >= 1");
@@ -178,10 +205,12 @@ extern "C" int derl_b200_relu_bwd_bias(const void* grad_out, const void* out, vo
   switch (dtype) {
     case DERL_DTYPE_BF16:
       return launch<__nv_bfloat16>(grad_out, out, grad_pre, bias_grad, rows, (int)channels,
-                                   workspace, st);
+                                   workspace, unblock, (int)blocked_height, (int)blocked_width, st);
     case DERL_DTYPE_F16:
-      return launch<__half>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace, st);
+      return launch<__half>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace,
+                            unblock, (int)blocked_height, (int)blocked_width, st);
     default:
-      return launch<float>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace, st);
+      return launch<float>(grad_out, out, grad_pre, bias_grad, rows, (int)channels, workspace,
+                           unblock, (int)blocked_height, (int)blocked_width, st);
   }
 }

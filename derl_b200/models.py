@@ -114,11 +114,11 @@ class _StemConvReLU(torch.autograd.Function):
   def backward(ctx, grad_out):
     frames, out = ctx.saved_tensors
     grad_out = grad_out.contiguous(memory_format=torch.channels_last)
-    grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out)
-    if ctx.out_block == 2:          # [B,128,10,10] (i, j, c) channels -> [B,32,20,20]
+    # out_block 2: [B,128,10,10] with (i, j, c) channels; K5 stores the masked gradient
+    # straight in the plain [B,32,20,20] layout the weight-gradient conv needs
+    grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out, ctx.out_block)
+    if ctx.out_block == 2:
       grad_b = grad_b.view(4, 32).sum(0)
-      grad_pre = torch.ops.derl_b200.space_to_depth(grad_pre.permute(0, 2, 3, 1), 2, True)
-      grad_pre = grad_pre.permute(0, 3, 1, 2)
     s2d = torch.ops.derl_b200.frames_to_s2d(frames, 4, out.dtype, 255.0).permute(0, 3, 1, 2)
     shape_only = s2d.new_empty((32, 64, 2, 2)).contiguous(memory_format=torch.channels_last)
     _, grad_w2, _ = torch.ops.aten.convolution_backward(

@@ -369,16 +369,24 @@ def _(frames, weight, bias, dtype, out_block=1):
 
 # --------------------------------------------------------------------------- K5: ReLU bwd
 @torch.library.custom_op("derl_b200::relu_bwd_bias", mutates_args=(), device_types="cuda")
-def relu_bwd_bias(grad_out: Tensor, out: Tensor) -> Tuple[Tensor, Tensor]:
+def relu_bwd_bias(grad_out: Tensor, out: Tensor, unblock: int = 1) -> Tuple[Tensor, Tensor]:
   """(grad_out masked by out > 0, per-channel sum of it as float32) for channels-last
-  [B, C, H, W] tensors — threshold_backward and the bias gradient in one pass."""
+  [B, C, H, W] tensors — threshold_backward and the bias gradient in one pass.  unblock > 1:
+  the inputs are a space-to-depth(unblock) arrangement; the masked gradient comes back in the
+  plain [B, C / unblock^2, H * unblock, W * unblock] layout, the sums keep C entries."""
   _need(grad_out.dim() == 4 and grad_out.shape == out.shape, "expected two [B, C, H, W] tensors")
   _need(grad_out.dtype == out.dtype and out.dtype in _S2D_DTYPES, "unsupported dtype")
   _need(out.is_contiguous(memory_format=torch.channels_last)
         and grad_out.is_contiguous(memory_format=torch.channels_last),
         "relu_bwd_bias needs channels_last tensors")
   batch, chans, height, width = out.shape
-  grad_pre = torch.empty_like(out)
+  if unblock > 1:
+    _need(chans % (4 * unblock * unblock) == 0, "channels must be a multiple of 4 * unblock^2")
+    grad_pre = torch.empty((batch, chans // unblock ** 2, height * unblock, width * unblock),
+                           dtype=out.dtype, device=out.device,
+                           memory_format=torch.channels_last)
+  else:
+    grad_pre = torch.empty_like(out)
   bias_grad = torch.empty(chans, dtype=torch.float32, device=out.device)
   lib = _lib.load()
   ws_bytes = lib.derl_b200_relu_bwd_bias_workspace_bytes(chans)
@@ -386,14 +394,17 @@ def relu_bwd_bias(grad_out: Tensor, out: Tensor) -> Tuple[Tensor, Tensor]:
   with _device_of(out, "relu_bwd_bias"):
     _lib.check(lib.derl_b200_relu_bwd_bias(_p(grad_out), _p(out), _p(grad_pre), _p(bias_grad),
                                            batch * height * width, chans,
-                                           _S2D_DTYPES[out.dtype], _p(ws), ws_bytes,
-                                           _stream(out)), "relu_bwd_bias")
+                                           _S2D_DTYPES[out.dtype], unblock, height, width,
+                                           _p(ws), ws_bytes, _stream(out)), "relu_bwd_bias")
   return grad_pre, bias_grad
 
 
 @relu_bwd_bias.register_fake
-def _(grad_out, out):
-  return torch.empty_like(out), out.new_empty(out.shape[1], dtype=torch.float32)
+def _(grad_out, out, unblock=1):
+  batch, chans, height, width = out.shape
+  shape = (batch, chans // unblock ** 2, height * unblock, width * unblock)
+  return (out.new_empty(shape).contiguous(memory_format=torch.channels_last),
+          out.new_empty(chans, dtype=torch.float32))
 
 
 # --------------------------------------------------------------------------- K3: PPO loss

@@ -233,10 +233,16 @@ int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const flo
  * Replaces, per conv layer of the reference's NatureCNNBase (derl/models.py:102-109), ATen's
  * threshold_backward plus the extra read cuDNN's convolution_backward spends on the bias
  * gradient.  dtype as DERL_DTYPE_*; bias_grad is float32; channels % 4 == 0 and channels/4
- * must divide 256; deterministic.  workspace >= derl_b200_relu_bwd_bias_workspace_bytes(C). */
+ * must divide 256; deterministic.  workspace >= derl_b200_relu_bwd_bias_workspace_bytes(C).
+ * unblock > 1: grad_out / out are the space-to-depth(unblock) arrangement
+ * [B, blocked_height, blocked_width, unblock^2 * c] of an activation (rows = B * blocked_height
+ * * blocked_width, channels = unblock^2 * c); grad_pre is then written in the PLAIN
+ * [B, blocked_height*unblock, blocked_width*unblock, c] layout (depth-to-space folded into the
+ * stores) and bias_grad still has `channels` entries ((i, j, c) order: fold over (i, j)). */
 size_t derl_b200_relu_bwd_bias_workspace_bytes(int64_t channels);
 int derl_b200_relu_bwd_bias(const void* grad_out_dev, const void* out_dev, void* grad_pre_dev,
                             float* bias_grad_dev, int64_t rows, int64_t channels, int dtype,
+                            int unblock, int64_t blocked_height, int64_t blocked_width,
                             void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer entry points

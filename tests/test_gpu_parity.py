@@ -644,6 +644,16 @@ def test_relu_backward_bias_kernel_vs_aten(dtype):
     assert torch.equal(again, bias)
   with pytest.raises(ValueError, match="channels_last"):
     K.relu_bwd_bias(torch.zeros(2, 8, 3, 3, device=DEV), torch.zeros(2, 8, 3, 3, device=DEV))
+  # unblock: inputs in space-to-depth(2) arrangement, masked gradient back in the plain layout
+  plain_out = torch.relu(torch.randn(9, 20, 20, 32, device=DEV, generator=gen)).to(dtype)
+  plain_grad = torch.randn(9, 20, 20, 32, device=DEV, generator=gen).to(dtype)
+  s2d = lambda x: K.space_to_depth(x, 2, False).permute(0, 3, 1, 2)
+  grad_pre, bias = K.relu_bwd_bias(s2d(plain_grad), s2d(plain_out), 2)
+  want = torch.ops.aten.threshold_backward(plain_grad, plain_out, 0)
+  assert grad_pre.shape == (9, 32, 20, 20)
+  assert torch.equal(grad_pre.permute(0, 2, 3, 1), want)
+  assert torch.allclose(bias.view(4, 32).sum(0).double(), want.double().sum((0, 1, 2)),
+                        rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
