@@ -2,7 +2,7 @@
 
   python tools/profile_kernels.py                       # plain run (must exit 0 first)
   ncu --set full --clock-control none --import-source on \
-      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns|frames_to_s2d|relu_bwd' -c 40 \
+      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns|frames_to_s2d|relu_bwd|stem_conv' -c 48 \
       -o gpurun_out/kernels python tools/profile_kernels.py
 
 Sizes: gather = one 131072-row minibatch out of a 4096x128 frame-stack rollout (14.8 GB,
@@ -81,6 +81,12 @@ def main():
     state["i"] = (state["i"] + 1) % 4
     return K.gather_rows(obs, perm, state["i"] * mb, mb)
   timed("gather_rows_tma 131072x28224", gather, (8 + 2 * 28224.0) * mb)
+  wstem = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * .1
+  bstem = torch.zeros(32, device=DEV)
+  for blk in (1, 2):
+    timed(f"stem_conv_relu 32768 f32 blk{blk}",
+          lambda: K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, blk),
+          32768 * (28224 + 400 * 32 * 4.0))
   frames = obs[:16384]
   for dt, nb in ((torch.float32, 5.0), (torch.bfloat16, 3.0)):
     timed(f"frames_to_s2d 16384 {str(dt)[6:]}", lambda: K.frames_to_s2d(frames, 4, dt, 255.0),
