@@ -6,7 +6,8 @@ there is no CPU fallback — without the library the import fails, without an sm
 every op raises.
 """
 from . import summary
-from .alg import Alg, GraphedTrainer, Loss, PPO, PPOLoss, Trainer, r_squared, total_norm
+from .alg import (A2C, A2CLoss, Alg, GraphedTrainer, Loss, PPO, PPOLoss, Trainer, r_squared,
+                  total_norm)
 from .anneal import AnnealingVariable, LinearAnneal
 from .models import MLP, MuJoCoModel, NatureCNNBase, NatureCNNModel, make_model, orthogonal_init
 from .policies import ActorCriticPolicy, Policy

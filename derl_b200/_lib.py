@@ -42,6 +42,10 @@ SIGNATURES = {
     "derl_b200_ppo_loss_gaussian": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr,
                                            _ptr, _int, _f64, _f64, _f64, _ptr, _ptr, _ptr, _ptr,
                                            _ptr, _ptr, _size, _ptr]),
+    "derl_b200_a2c_loss_categorical": (_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _f64, _f64,
+                                              _ptr, _ptr, _ptr, _ptr, _ptr, _size, _ptr]),
+    "derl_b200_a2c_loss_gaussian": (_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _f64,
+                                           _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _size, _ptr]),
     "derl_b200_frames_to_s2d": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _f64, _ptr]),
     "derl_b200_relu_bwd_bias_workspace_bytes": (_size, [_i64]),
     "derl_b200_relu_bwd_bias": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _int, _i64, _i64,

@@ -19,11 +19,12 @@
 namespace derl {
 namespace {
 
-constexpr int kAcc = 10;
-enum { kPol = 0, kEnt, kVal, kAdv, kVt, kV, kVsq, kResid, kClipFrac, kKl };
+constexpr int kAcc = 11;
+enum { kPol = 0, kEnt, kVal, kAdv, kVt, kV, kVsq, kResid, kClipFrac, kKl, kVtsq };
 
 struct LossScalars {
   long long B;
+  int a2c;               // 1: advantage actor-critic policy term -log_prob * adv (derl/alg/a2c.py:31)
   int has_clip;
   float lo, hi, vclip;   // 1-clip, 1+clip, clip (rounded to float32 like torch.clamp's scalars)
   float inv_b;           // 1 / B
@@ -33,6 +34,11 @@ struct LossScalars {
 // d loss / d log_prob for one sample (includes 1/B); accumulates the policy-side sums.
 __device__ __forceinline__ float surrogate(float lp, float old_lp, float adv,
                                            const LossScalars& k, double (&acc)[kAcc]) {
+  if (k.a2c) {
+    acc[kPol] += (double)(-(lp * adv));
+    acc[kAdv] += (double)adv;
+    return -adv * k.inv_b;
+  }
   const float ratio = expf(lp - old_lp);
   const float s1 = -ratio * adv;
   float pol = s1, w = 1.f;
@@ -69,6 +75,7 @@ __device__ __forceinline__ float value_term(float v, float vt, float vold, const
   acc[kVt] += (double)vt;
   acc[kV] += (double)v;
   acc[kVsq] += (double)v * (double)v;
+  acc[kVtsq] += (double)vt * (double)vt;
   acc[kResid] += (double)l1;
   return dv;
 }
@@ -88,8 +95,11 @@ __device__ __forceinline__ void finish_loss(double (&acc)[kAcc], const LossScala
   double total = 0.0;
   if (has_policy) total += pol - k.ecoef * ent;
   if (has_value) total += k.vcoef * val;
+  // r_squared(targets, predictions) = 1 - mean((p - t)^2) / var_unbiased(p)   (alg/common.py:9-12);
+  // PPO passes predictions = values (ppo.py:94), A2C passes predictions = value_targets (a2c.py:62)
   const double mean_v = tot[kV] / b;
-  const double var_v = (tot[kVsq] - b * mean_v * mean_v) / (b - 1.0);  // Bessel, like torch.std
+  const double mean_p = (k.a2c ? tot[kVt] : tot[kV]) / b;
+  const double var_v = ((k.a2c ? tot[kVtsq] : tot[kVsq]) - b * mean_p * mean_p) / (b - 1.0);
   loss[0] = (float)total;
   stats[0] = (float)total;
   stats[1] = (float)pol;
@@ -163,7 +173,7 @@ ppo_loss_categorical_kernel(const float* __restrict__ logits, int A,
           h -= (expf(z[c] - m) * inv_s) * fmaxf(ln, -3.4028234663852886e38f);
         }
         acc[kEnt] += (double)h;
-        const float g = surrogate(lp, __ldg(old_logp + i), __ldg(adv + i), k, acc);
+        const float g = surrogate(lp, k.a2c ? 0.f : __ldg(old_logp + i), __ldg(adv + i), k, acc);
         const float ce = (float)k.ecoef * k.inv_b;
         for (int c = 0; c < A; ++c) {
           const float ln = z[c] - lse;
@@ -176,7 +186,8 @@ ppo_loss_categorical_kernel(const float* __restrict__ logits, int A,
       __syncthreads();
     }
     if (has_value && live) {
-      const float dv = value_term(__ldg(values + i), __ldg(vtarg + i), __ldg(vold + i), k, acc);
+      const float dv = value_term(__ldg(values + i), __ldg(vtarg + i),
+                                  k.has_clip ? __ldg(vold + i) : 0.f, k, acc);
       dvalues[i] = (float)k.vcoef * k.inv_b * dv;
     }
   }
@@ -228,7 +239,7 @@ ppo_loss_gaussian_kernel(const float* __restrict__ loc, const float* __restrict_
           h += kHalfLog2PiE + log_sd;
         }
         acc[kEnt] += (double)h;
-        const float g = surrogate(lp, __ldg(old_logp + i), __ldg(adv + i), k, acc);
+        const float g = surrogate(lp, k.a2c ? 0.f : __ldg(old_logp + i), __ldg(adv + i), k, acc);
         const float ce = (float)k.ecoef * k.inv_b;
         for (int c = 0; c < D; ++c) {
           const float sd = sg[c], diff = ac[c] - mu[c];
@@ -244,16 +255,19 @@ ppo_loss_gaussian_kernel(const float* __restrict__ loc, const float* __restrict_
       __syncthreads();
     }
     if (has_value && live) {
-      const float dv = value_term(__ldg(values + i), __ldg(vtarg + i), __ldg(vold + i), k, acc);
+      const float dv = value_term(__ldg(values + i), __ldg(vtarg + i),
+                                  k.has_clip ? __ldg(vold + i) : 0.f, k, acc);
       dvalues[i] = (float)k.vcoef * k.inv_b * dv;
     }
   }
   finish_loss(acc, k, has_policy, has_value, workspace, loss, stats, scratch, &flag);
 }
 
-LossScalars make_scalars(long long B, int has_clip, double clip, double vcoef, double ecoef) {
+LossScalars make_scalars(long long B, int has_clip, double clip, double vcoef, double ecoef,
+                         int a2c = 0) {
   LossScalars k;
   k.B = B;
+  k.a2c = a2c;
   k.has_clip = has_clip ? 1 : 0;
   k.lo = (float)(1.0 - clip);
   k.hi = (float)(1.0 + clip);
@@ -286,12 +300,16 @@ unsigned loss_grid(long long B, int R) {
 int check_common(const char* who, long long B, const void* head, const float* old_logp,
                  const float* adv, const float* values, const float* vtarg, const float* vold,
                  const void* dvalues, const float* loss, const float* stats, void* workspace,
-                 size_t workspace_bytes) {
+                 size_t workspace_bytes, int a2c = 0, int has_clip = 1) {
   DERL_REQUIRE(B >= 1, "%s: B must be >= 1 (got %lld)", who, B);
   DERL_REQUIRE(head != nullptr || values != nullptr, "%s: both heads are NULL", who);
-  if (head != nullptr) DERL_REQUIRE(old_logp && adv, "%s: policy head needs old_logp and advantages", who);
+  if (head != nullptr) {
+    DERL_REQUIRE(adv != nullptr, "%s: policy head needs advantages", who);
+    DERL_REQUIRE(a2c || old_logp != nullptr, "%s: policy head needs old_logp", who);
+  }
   if (values != nullptr) {
-    DERL_REQUIRE(vtarg && vold && dvalues, "%s: value head needs value_targets, old_values, dvalues", who);
+    DERL_REQUIRE(vtarg && dvalues, "%s: value head needs value_targets and dvalues", who);
+    DERL_REQUIRE(!has_clip || vold != nullptr, "%s: clipped value loss needs old_values", who);
   } else {
     DERL_REQUIRE(dvalues == nullptr, "%s: dvalues given without values", who);
   }
@@ -387,6 +405,77 @@ int derl_b200_ppo_loss_gaussian(const float* loc, const float* scale, int64_t B,
       loc, scale, (int)D, actions, old_logp, adv, values, vtarg, vold,
       make_scalars(B, has_clip, clip, vcoef, ecoef), loss, dloc, dscale, dvalues, stats,
       workspace);
+  DERL_LAUNCH_CHECK("ppo_loss_gaussian_kernel");
+  return DERL_OK;
+}
+
+/* Advantage actor-critic loss (derl/alg/a2c.py:19-79) on the same kernels: policy term
+ * -mean(log_prob * adv), unclipped value loss, same entropy term, gradients and logged scalars. */
+int derl_b200_a2c_loss_categorical(const float* logits, int64_t B, int64_t A,
+                                   const int64_t* actions, const float* adv, const float* values,
+                                   const float* vtarg, double vcoef, double ecoef, float* loss,
+                                   float* dlogits, float* dvalues, float* stats, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  int rc = check_common("a2c_loss_categorical", B, logits, nullptr, adv, values, vtarg, nullptr,
+                        dvalues, loss, stats, workspace, workspace_bytes, 1, 0);
+  if (rc != DERL_OK) return rc;
+  if (logits != nullptr) {
+    DERL_REQUIRE(A >= 1 && A <= 1024, "a2c_loss_categorical: A=%lld outside [1, 1024]",
+                 (long long)A);
+    DERL_REQUIRE(actions && dlogits, "a2c_loss_categorical: actions/dlogits are NULL");
+  } else {
+    DERL_REQUIRE(dlogits == nullptr, "a2c_loss_categorical: dlogits given without logits");
+    A = 1;
+  }
+  if ((rc = require_device()) != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  size_t smem = 0;
+  const int R = pick_rows(A, 1, &smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_categorical_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
+    attr_set = true;
+  }
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
+      logits, (int)A, reinterpret_cast<const long long*>(actions), nullptr, adv, values, vtarg,
+      nullptr, make_scalars(B, 0, 0.0, vcoef, ecoef, 1), loss, dlogits, dvalues, stats, workspace);
+  DERL_LAUNCH_CHECK("ppo_loss_categorical_kernel");
+  return DERL_OK;
+}
+
+int derl_b200_a2c_loss_gaussian(const float* loc, const float* scale, int64_t B, int64_t D,
+                                const float* actions, const float* adv, const float* values,
+                                const float* vtarg, double vcoef, double ecoef, float* loss,
+                                float* dloc, float* dscale, float* dvalues, float* stats,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("a2c_loss_gaussian", B, loc, nullptr, adv, values, vtarg, nullptr,
+                        dvalues, loss, stats, workspace, workspace_bytes, 1, 0);
+  if (rc != DERL_OK) return rc;
+  if (loc != nullptr) {
+    DERL_REQUIRE(D >= 1 && D <= 256, "a2c_loss_gaussian: D=%lld outside [1, 256]", (long long)D);
+    DERL_REQUIRE(scale && actions && dloc && dscale,
+                 "a2c_loss_gaussian: scale/actions/dloc/dscale are NULL");
+  } else {
+    DERL_REQUIRE(dloc == nullptr && dscale == nullptr,
+                 "a2c_loss_gaussian: gradients given without loc");
+    D = 1;
+  }
+  if ((rc = require_device()) != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  size_t smem = 0;
+  const int R = pick_rows(D, 3, &smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_gaussian_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
+    attr_set = true;
+  }
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
+      loc, scale, (int)D, actions, nullptr, adv, values, vtarg, nullptr,
+      make_scalars(B, 0, 0.0, vcoef, ecoef, 1), loss, dloc, dscale, dvalues, stats, workspace);
   DERL_LAUNCH_CHECK("ppo_loss_gaussian_kernel");
   return DERL_OK;
 }

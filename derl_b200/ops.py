@@ -552,3 +552,121 @@ def _gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
 
 
 ppo_loss_gaussian.register_autograd(_gauss_backward, setup_context=_gauss_setup)
+
+
+# --------------------------------------------------------------------------- A2C loss
+@torch.library.custom_op("derl_b200::a2c_loss_categorical", mutates_args=(), device_types="cuda")
+def a2c_loss_categorical(logits: Optional[Tensor], values: Optional[Tensor],
+                         actions: Optional[Tensor], advantages: Optional[Tensor],
+                         value_targets: Optional[Tensor], value_loss_coef: float,
+                         entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+  """Advantage actor-critic loss (categorical head): (loss [], dlogits, dvalues, stats f32[16])."""
+  ref = logits if logits is not None else values
+  _need(ref is not None, "a2c_loss: both heads are absent")
+  nb, nact = ref.shape[0], 1
+  if logits is not None:
+    _dense(logits, "logits", (torch.float32,))
+    _need(logits.dim() == 2 and actions is not None and advantages is not None,
+          "a2c_loss_categorical: logits must be [B, A] with actions and advantages")
+    _dense(actions, "actions", (torch.int64,))
+    _dense(advantages, "advantages", (torch.float32,))
+    _need(actions.numel() == nb and advantages.numel() == nb, "one action / advantage per sample")
+    nact = logits.shape[1]
+  if values is not None:
+    _need(value_targets is not None, "a2c_loss: value head needs value_targets")
+    _dense(values, "values", (torch.float32,))
+    _dense(value_targets, "value_targets", (torch.float32,))
+    _need(values.numel() == nb and value_targets.numel() == nb, "one value / target per sample")
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  dlogits = torch.empty_like(logits) if logits is not None else ref.new_empty(0)
+  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
+  with _device_of(ref, "a2c_loss_categorical"):
+    _lib.check(lib.derl_b200_a2c_loss_categorical(
+        _p(logits), nb, nact, _p(actions), _p(advantages), _p(values), _p(value_targets),
+        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dlogits), _p(dvalues),
+        _p(stats), _p(ws), ws_bytes, _stream(ref)), "a2c_loss_categorical")
+  return loss, dlogits, dvalues, stats
+
+
+@a2c_loss_categorical.register_fake
+def _(logits, values, actions, advantages, value_targets, value_loss_coef, entropy_coef):
+  ref = logits if logits is not None else values
+  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
+  return ref.new_empty(()), grad(logits), grad(values), ref.new_empty(_lib.LOSS_STATS)
+
+
+def _a2c_cat_setup(ctx, inputs, output):
+  ctx.set_materialize_grads(False)
+  ctx.save_for_backward(output[1], output[2])
+  ctx.has = (inputs[0] is not None, inputs[1] is not None)
+
+
+def _a2c_cat_backward(ctx, g_loss, g_dlogits, g_dvalues, g_stats):
+  dlogits, dvalues = ctx.saved_tensors
+  rest = (None,) * 5
+  if g_loss is None:
+    return (None, None) + rest
+  return ((g_loss * dlogits) if ctx.has[0] else None,
+          (g_loss * dvalues) if ctx.has[1] else None) + rest
+
+
+a2c_loss_categorical.register_autograd(_a2c_cat_backward, setup_context=_a2c_cat_setup)
+
+
+@torch.library.custom_op("derl_b200::a2c_loss_gaussian", mutates_args=(), device_types="cuda")
+def a2c_loss_gaussian(loc: Optional[Tensor], scale: Optional[Tensor], values: Optional[Tensor],
+                      actions: Optional[Tensor], advantages: Optional[Tensor],
+                      value_targets: Optional[Tensor], value_loss_coef: float,
+                      entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+  """Advantage actor-critic loss (diagonal-Gaussian head)."""
+  ref = loc if loc is not None else values
+  _need(ref is not None, "a2c_loss: both heads are absent")
+  nb, ndim = ref.shape[0], 1
+  if loc is not None:
+    _need(scale is not None and actions is not None and advantages is not None,
+          "a2c_loss_gaussian: scale / actions / advantages missing")
+    for name, t in (("loc", loc), ("scale", scale), ("actions", actions),
+                    ("advantages", advantages)):
+      _dense(t, name, (torch.float32,))
+    _need(loc.dim() == 2 and scale.shape == loc.shape and actions.shape == loc.shape
+          and advantages.numel() == nb, "loc, scale, actions must be [B, D]; one advantage per row")
+    ndim = loc.shape[1]
+  if values is not None:
+    _need(value_targets is not None, "a2c_loss: value head needs value_targets")
+    _dense(values, "values", (torch.float32,))
+    _dense(value_targets, "value_targets", (torch.float32,))
+    _need(values.numel() == nb and value_targets.numel() == nb, "one value / target per sample")
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
+  dloc, dscale, dvalues = grad(loc), grad(scale if loc is not None else None), grad(values)
+  with _device_of(ref, "a2c_loss_gaussian"):
+    _lib.check(lib.derl_b200_a2c_loss_gaussian(
+        _p(loc), _p(scale), nb, ndim, _p(actions), _p(advantages), _p(values), _p(value_targets),
+        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc), _p(dscale), _p(dvalues),
+        _p(stats), _p(ws), ws_bytes, _stream(ref)), "a2c_loss_gaussian")
+  return loss, dloc, dscale, dvalues, stats
+
+
+@a2c_loss_gaussian.register_fake
+def _(loc, scale, values, actions, advantages, value_targets, value_loss_coef, entropy_coef):
+  ref = loc if loc is not None else values
+  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
+  return ref.new_empty(()), grad(loc), grad(scale), grad(values), ref.new_empty(_lib.LOSS_STATS)
+
+
+def _a2c_gauss_setup(ctx, inputs, output):
+  ctx.set_materialize_grads(False)
+  ctx.save_for_backward(output[1], output[2], output[3])
+  ctx.has = (inputs[0] is not None, inputs[2] is not None)
+
+
+def _a2c_gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
+  dloc, dscale, dvalues = ctx.saved_tensors
+  rest = (None,) * 5
+  if g_loss is None:
+    return (None, None, None) + rest
+  return ((g_loss * dloc) if ctx.has[0] else None, (g_loss * dscale) if ctx.has[0] else None,
+          (g_loss * dvalues) if ctx.has[1] else None) + rest
+
+
+a2c_loss_gaussian.register_autograd(_a2c_gauss_backward, setup_context=_a2c_gauss_setup)

@@ -188,6 +188,24 @@ int derl_b200_ppo_loss_gaussian(const float* loc_dev, const float* scale_dev, in
                                 float* dscale_dev, float* dvalues_dev, float* stats_dev,
                                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Advantage actor-critic loss on the same kernels: replaces
+ * A2CLoss.__call__ (derl/alg/a2c.py:19-79): policy term -mean(log_prob * adv) (:31), unclipped
+ * value loss mean((v - vt)^2) (:56), entropy (:32); stats as for PPO except [7] =
+ * r_squared(values, value_targets) with the reference's argument order (:62), [8] = [9] = 0. */
+int derl_b200_a2c_loss_categorical(const float* logits_dev, int64_t B, int64_t A,
+                                   const int64_t* actions_dev, const float* advantages_dev,
+                                   const float* values_dev, const float* value_targets_dev,
+                                   double value_loss_coef, double entropy_coef, float* loss_dev,
+                                   float* dlogits_dev, float* dvalues_dev, float* stats_dev,
+                                   void* workspace_dev, size_t workspace_bytes, void* stream);
+int derl_b200_a2c_loss_gaussian(const float* loc_dev, const float* scale_dev, int64_t B,
+                                int64_t D, const float* actions_dev, const float* advantages_dev,
+                                const float* values_dev, const float* value_targets_dev,
+                                double value_loss_coef, double entropy_coef, float* loss_dev,
+                                float* dloc_dev, float* dscale_dev, float* dvalues_dev,
+                                float* stats_dev, void* workspace_dev, size_t workspace_bytes,
+                                void* stream);
+
 /* ------------------------------------------------------------------ K4: frame preparation
  * Replaces the input pipeline of NatureCNNBase.forward (derl/models.py:117-123: NHWC->NCHW
  * permute, `.float() / 255`, `.contiguous()`) with one pass that also applies the

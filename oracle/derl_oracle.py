@@ -217,6 +217,27 @@ def ppo_loss(dist_inputs, values, batch, cliprange=0.2, value_loss_coef=0.25,
   return loss
 
 
+def a2c_loss(dist_inputs, values, batch, value_loss_coef=0.25, entropy_coef=0.01,
+             return_parts=False):
+  """A2CLoss.__call__ on CPU torch, derl/alg/a2c.py:19-79."""
+  def t(x):
+    return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.asarray(x))
+  dist = make_distribution(*dist_inputs)
+  adv, targets = t(batch["advantages"]), t(batch["value_targets"])
+  log_prob = dist.log_prob(t(batch["actions"]))                       # :23-24
+  policy_loss = -torch.mean(log_prob * adv)                           # :32
+  entropy = torch.mean(dist.entropy())                                # :33
+  value_loss = torch.mean(torch.pow(values - targets, 2))             # :57
+  loss = (policy_loss - entropy_coef * entropy) + value_loss_coef * value_loss   # :44, :72
+  if return_parts:
+    target_var = torch.pow(targets.std(), 2)   # r_squared(values, value_targets): args as in :62
+    return loss, dict(loss=loss, policy_loss=policy_loss, entropy=entropy, value_loss=value_loss,
+                      advantages=torch.mean(adv), value_targets=torch.mean(targets),
+                      value_preds=torch.mean(values),
+                      r_squared=1. - torch.mean(torch.pow(targets - values, 2)) / target_var)
+  return loss
+
+
 def ppo_loss_closed_form(dist_inputs, values, batch, cliprange=0.2, value_loss_coef=0.25,
                          entropy_coef=0.01):
   """Second, autograd-free statement (float64 NumPy) of the loss and of its gradients with

@@ -259,6 +259,45 @@ def live_ppo_loss():
   save("live_ppo_loss.npz", **out)
 
 
+def live_a2c_loss():
+  """A2CLoss forward/backward + logged scalars (derl/alg/a2c.py) on both heads."""
+  rng = np.random.RandomState(777)
+  out = {}
+  specs = [("categorical", 129, 6, .5, .01), ("gaussian", 77, 3, .25, .02),
+           ("categorical", 40, 18, 1., 0.)]
+  for i, (kind, nbatch, width, vcoef, ecoef) in enumerate(specs):
+    adv = rng.randn(nbatch).astype(np.float32)
+    values = rng.randn(nbatch, 1).astype(np.float32)
+    targets = (values + rng.randn(nbatch, 1)).astype(np.float32)
+    if kind == "categorical":
+      head = [(rng.randn(nbatch, width) * 2).astype(np.float32)]
+      actions = rng.randint(0, width, nbatch).astype(np.int64)
+    else:
+      head = [rng.randn(nbatch, width).astype(np.float32),
+              np.exp(rng.randn(nbatch, width) * .3).astype(np.float32)]
+      actions = (head[0] + rng.randn(nbatch, width) * head[1]).astype(np.float32)
+    batch = dict(actions=actions, advantages=adv, value_targets=targets)
+    leaves = [torch.tensor(h, requires_grad=True) for h in head]
+    v_leaf = torch.tensor(values, requires_grad=True)
+    loss_fn = derl.A2CLoss(HeadPolicy(leaves, v_leaf), value_loss_coef=vcoef, entropy_coef=ecoef)
+    log = ScalarLog()
+    ref_summary.set_writer(log)
+    ref_summary.start_recording()
+    loss = loss_fn(batch)
+    ref_summary.stop_recording()
+    loss.backward()
+    case = dict(batch, kind=kind, vcoef=vcoef, ecoef=ecoef, pred_values=values,
+                loss=loss.detach().numpy(), dvalues=v_leaf.grad.numpy())
+    for j, (h, leaf) in enumerate(zip(head, leaves)):
+      case[f"head{j}"], case[f"dhead{j}"] = h, leaf.grad.numpy()
+    for tag, val in log.scalars.items():
+      case["log_" + tag.replace("/", "_")] = np.float32(val)
+    for key, val in case.items():
+      out[f"c{i}_{key}"] = val
+  out["ncases"] = len(specs)
+  save("live_a2c_loss.npz", **out)
+
+
 # ----------------------------------------------------------------------------- live full update
 def live_update(name, kind):
   """Seeded model + synthetic rollouts through the reference's whole PPO pipeline:
@@ -325,6 +364,7 @@ def main():
   live_gae()
   live_minibatches()
   live_ppo_loss()
+  live_a2c_loss()
   live_update("live_update_mujoco.npz", "mujoco")
   live_update("live_update_atari.npz", "atari")
 

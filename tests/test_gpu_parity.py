@@ -476,6 +476,41 @@ def test_ppo_loss_golden_forward_backward_and_scalars(golden):
     np.testing.assert_allclose(fn2.value_loss(batch).item(), c["value_loss"], rtol=1e-5)
 
 
+def test_a2c_loss_golden_forward_backward_and_scalars(golden):
+  """A2CLoss on the fused kernels (a2c mode) against the reference's A2CLoss + autograd
+  (tests/golden/live_a2c_loss.npz), both heads, incl. the logged scalars."""
+  g = golden("live_a2c_loss.npz")
+  for i in range(g.ncases):
+    c = g.case(i)
+    head = [cuda(c[f"head{j}"]).requires_grad_() for j in range(2) if f"head{j}" in c]
+    values = cuda(c["pred_values"]).requires_grad_()
+    batch = {k: c[k] for k in ("actions", "advantages", "value_targets")}
+    fn = d.A2CLoss(HeadPolicy(head, values), value_loss_coef=float(c["vcoef"]),
+                   entropy_coef=float(c["ecoef"]))
+    assert fn.name == "a2c"
+    loss = fn(batch)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), c["loss"], rtol=1e-5, err_msg=f"case {i}")
+    np.testing.assert_allclose(values.grad.cpu().numpy(), c["dvalues"], rtol=1e-5,
+                               atol=1e-5 * np.abs(c["dvalues"]).max())
+    for j, h in enumerate(head):
+      want = c[f"dhead{j}"]
+      np.testing.assert_allclose(h.grad.cpu().numpy(), want, rtol=1e-5,
+                                 atol=1e-5 * np.abs(want).max(), err_msg=f"case {i} head{j}")
+    stats = fn.last_stats.cpu().numpy()
+    for key in ("loss", "policy_loss", "entropy", "value_loss", "advantages", "value_targets",
+                "value_preds", "r_squared"):
+      np.testing.assert_allclose(stats[d.alg.ppo.STAT[key]], c[f"log_a2c_{key}"], rtol=2e-5,
+                                 atol=2e-7, err_msg=f"case {i} {key}")
+    head2 = [cuda(c[f"head{j}"]) for j in range(2) if f"head{j}" in c]
+    fn2 = d.A2CLoss(HeadPolicy(head2, cuda(c["pred_values"])), value_loss_coef=float(c["vcoef"]),
+                    entropy_coef=float(c["ecoef"]))
+    np.testing.assert_allclose(fn2.value_loss(batch).item(), c["log_a2c_value_loss"], rtol=1e-5)
+    np.testing.assert_allclose(
+        fn2.policy_loss(batch).item(),
+        c["log_a2c_policy_loss"] - float(c["ecoef"]) * c["log_a2c_entropy"], rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("kind,width", [("categorical", 4), ("categorical", 18),
                                         ("categorical", 130), ("gaussian", 6),
                                         ("gaussian", 40)])
