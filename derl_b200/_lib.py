@@ -52,6 +52,8 @@ SIGNATURES = {
                                        _ptr, _size, _ptr]),
     "derl_b200_stem_conv_relu": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _ptr]),
     "derl_b200_space_to_depth": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
+    "derl_b200_stem_backward_workspace_bytes": (_size, []),
+    "derl_b200_stem_backward": (_int, [_ptr, _i64, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _size, _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,
                                   _f64, _ptr, _ptr, _ptr]),
 }

@@ -1,0 +1,358 @@
+// K7 — backward of the NatureCNN stem, straight from the uint8 frames on the INT8 tensor cores.
+//
+// Replaces, for the reference's first layer (derl/models.py:102-103: nn.Conv2d(4, 32, 8, 4) +
+// nn.ReLU), the three-pass backward K5 (ReLU mask + bias gradient) -> K4 (re-create the float32
+// space-to-depth frames) -> cuDNN wgrad with ONE kernel that reads, per frame, the raw 28 224
+// bytes, the incoming gradient and the saved activation (for the ReLU mask) exactly once:
+//     g[p, n]     = out[p, n] > 0 ? grad_out[p, n] : 0                       (400 pixels x 32)
+//     dbias[n]   += sum_p g[p, n]
+//     dW[n, c, 4a+i, 4b+j] += (1/255) * sum_{oy,ox} x[4(oy+a)+i, 4(ox+b)+j, c] * g[(oy,ox), n]
+// The frame operand is uint8 and exact; the gradient is quantised per (frame, channel) to two
+// signed 8-bit digit planes (block floating point): s = max_p |g[p, n]| / 127,
+// g ~= s * (q1 + q2 / 254), residual <= s / 508.  mma.sync m16n8k32 s8 x u8 -> s32 accumulates
+// each frame exactly; the int32 tile is then scaled and added to fp32 running sums.
+//   GEMM view per frame and per kernel quadrant (a, b):  D[32 ch x 64 taps] += Gq^T [32 x 400]
+//   * Z_ab [400 x 64], reduction over the output pixels.  MMA packs 4 consecutive reduction
+//   indices per register, so both operands are laid out pixel-fastest in shared memory:
+//   Gq[plane][channel][pixel] (written by the quantiser) and Zt[tap][Y][X], a byte transpose of
+//   the space-to-depth(4) frame (4x4 byte blocks, PRMT), in which 4 consecutive output pixels of
+//   one row are 4 consecutive bytes.
+//   One CTA (8 warps) per SM loops over frames; warp w owns quadrant w/2 and 32 of its taps.
+//   Inputs arrive by TMA bulk copies; the next frame's copies are in flight during the MMAs.
+// Per-CTA partial sums are reduced (fixed order) and re-indexed to [32, 4, 8, 8] by a second
+// small kernel.
+#include "common.cuh"
+
+namespace derl {
+namespace {
+
+constexpr int kFrameBytes = 84 * 84 * 4;      // 28224
+constexpr int kPix = 400, kCh = 32;           // output pixels, output channels
+constexpr int kTileBytes = kPix * kCh * 4;    // 51200: one frame's [400 x 32] float32 tile
+constexpr int kQuads = 100;                   // 4 consecutive ox of one oy
+constexpr int kSteps = 13;                    // ceil(100 quads / 8 quads per k32 step)
+constexpr int kGqPitch = 420;                 // bytes per (plane, channel) row: 105 words (odd)
+constexpr int kZtRow = 24, kZtTap = 21 * kZtRow;   // Zt[tap][Y (21)][X (24, 21 used)]
+constexpr int kWarps = 8, kThreads = kWarps * 32;
+
+struct BwdSmem {
+  static constexpr size_t frame_off = 0;                              // [2][28224] u8
+  static constexpr size_t grad_off = frame_off + 2 * (size_t)kFrameBytes + 64;   // float [400][32]
+  static constexpr size_t out_off = grad_off + kTileBytes;            // float [400][32]
+  static constexpr size_t zt_off = out_off + kTileBytes;              // u8 [64][504]
+  static constexpr size_t gq_off = zt_off + 64 * (size_t)kZtTap;      // s8 [2][32][420]
+  static constexpr size_t red_off = gq_off + 2 * kCh * (size_t)kGqPitch;  // float [8][32]
+  static constexpr size_t scale_off = red_off + 8 * kCh * 4;          // float [32]
+  static constexpr size_t bar_off = scale_off + kCh * 4;              // 3 mbarriers
+  static constexpr size_t bytes = bar_off + 32;
+};
+
+__device__ __forceinline__ void mma_s8u8(int (&d)[4], const unsigned (&a)[4], unsigned b0,
+                                         unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// index of output pixel (oy, ox) inside a frame's [400 x 32] tile, in units of pixels
+__device__ __forceinline__ int tile_pixel(int oy, int ox, int blocked) {
+  if (blocked) return (((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
+  return oy * 20 + ox;
+}
+
+// rint(x) for |x| < 2^22 and its two's-complement low byte, without the conversion pipe
+__device__ __forceinline__ float round_magic(float x, unsigned* bits) {
+  const float m = x + 12582912.f;   // 1.5 * 2^23
+  *bits = __float_as_uint(m);
+  return m - 12582912.f;
+}
+
+// grad_out / out: [B, 400, 32] float32 tiles (plain pixel order, or space-to-depth(2) order when
+// blocked != 0); partial_w: [grid][4 quadrants][64 taps][32 ch]; partial_b: [grid][32].
+__global__ void __launch_bounds__(kThreads, 1)
+stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ grad_out,
+                const float* __restrict__ out, float* __restrict__ partial_w,
+                float* __restrict__ partial_b, long long batch, int blocked) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* sg = reinterpret_cast<float*>(smem + BwdSmem::grad_off);
+  float* so = reinterpret_cast<float*>(smem + BwdSmem::out_off);
+  uint8_t* zt = smem + BwdSmem::zt_off;
+  uint8_t* gq = smem + BwdSmem::gq_off;
+  float* red = reinterpret_cast<float*>(smem + BwdSmem::red_off);
+  float* scale = reinterpret_cast<float*>(smem + BwdSmem::scale_off);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar_off);  // [0,1] frames, [2] tiles
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long first = blockIdx.x, stride = gridDim.x;
+
+  auto load_frame = [&](long long f, int buf) {
+    mbar_expect_tx(&bar[buf], kFrameBytes);
+    bulk_g2s(smem + BwdSmem::frame_off + (size_t)buf * kFrameBytes, frames + f * kFrameBytes,
+             kFrameBytes, &bar[buf]);
+  };
+  auto load_tiles = [&](long long f) {
+    mbar_expect_tx(&bar[2], 2 * kTileBytes);
+    bulk_g2s(sg, grad_out + f * (kPix * kCh), kTileBytes, &bar[2]);
+    bulk_g2s(so, out + f * (kPix * kCh), kTileBytes, &bar[2]);
+  };
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
+    mbar_fence_init();
+    if (first < batch) {
+      load_frame(first, 0);
+      load_tiles(first);
+    }
+    if (first + stride < batch) load_frame(first + stride, 1);
+  }
+  // zero the quantised-gradient buffer once: its padding (quads 100..104) must stay zero
+  for (int i = tid; i < 2 * kCh * kGqPitch / 4; i += kThreads) {
+    reinterpret_cast<unsigned*>(gq)[i] = 0u;
+  }
+  __syncthreads();
+
+  // ---- loop-invariant roles
+  const int quadrant = warp >> 1;                 // (a, b) = (quadrant >> 1, quadrant & 1)
+  const int qa = quadrant >> 1, qb = quadrant & 1;
+  const int tap0 = (warp & 1) * 32;               // this warp's 32 taps: tap0 + 8*nt + g
+  const int ch = tid & 31, sub = tid >> 5;        // quantiser role: channel, pixel subset (8)
+
+  float wsum[2][4][4];                            // [m-tile][n-tile][c-frag] fp32 running sums
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wsum[m][n][k] = 0.f;
+  float bsum = 0.f;
+
+  int it = 0;
+  for (long long f = first; f < batch; f += stride, ++it) {
+    const int buf = it & 1;
+    const uint8_t* raw = smem + BwdSmem::frame_off + (size_t)buf * kFrameBytes;
+    mbar_wait(&bar[buf], (unsigned)((it >> 1) & 1));
+    mbar_wait(&bar[2], (unsigned)(it & 1));
+
+    // ---- (1) byte transpose of the frame: Zt[(i*4+j)*4+c][Y][X] = raw[4Y+i][4X+j][c]
+    // one 4x4 byte block per step: 4 source words (X..X+3, channels c=0..3 each) ->
+    // 4 destination words (taps c=0..3, bytes X..X+3)
+    for (int blk = tid; blk < 21 * 16 * 6; blk += kThreads) {
+      const int xg = blk % 6, ij = (blk / 6) & 15, Y = blk / 96;
+      const int i = ij >> 2, j = ij & 3;
+      const uint8_t* src = raw + (4 * Y + i) * 336 + (16 * xg + j) * 4;
+      unsigned w0 = *reinterpret_cast<const unsigned*>(src);
+      unsigned w1 = *reinterpret_cast<const unsigned*>(src + 16);
+      unsigned w2 = *reinterpret_cast<const unsigned*>(src + 32);
+      unsigned w3 = *reinterpret_cast<const unsigned*>(src + 48);
+      // 4x4 byte transpose (rows w0..w3, columns = channel bytes)
+      const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
+      const unsigned t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
+      const unsigned c0 = __byte_perm(t0, t2, 0x5410), c1 = __byte_perm(t0, t2, 0x7632);
+      const unsigned c2 = __byte_perm(t1, t3, 0x5410), c3 = __byte_perm(t1, t3, 0x7632);
+      uint8_t* dst = zt + (ij * 4) * kZtTap + Y * kZtRow + 4 * xg;
+      *reinterpret_cast<unsigned*>(dst) = c0;
+      *reinterpret_cast<unsigned*>(dst + kZtTap) = c1;
+      *reinterpret_cast<unsigned*>(dst + 2 * kZtTap) = c2;
+      *reinterpret_cast<unsigned*>(dst + 3 * kZtTap) = c3;
+    }
+
+    // ---- (2) ReLU mask, per-channel max and bias sum: thread = (channel, one of 8 pixel subsets)
+    float vmax = 0.f, vsum = 0.f;
+    for (int p = sub; p < kPix; p += 8) {
+      const float gv = so[p * kCh + ch] > 0.f ? sg[p * kCh + ch] : 0.f;
+      vmax = fmaxf(vmax, fabsf(gv));
+      vsum += gv;
+    }
+    bsum += vsum;
+    red[sub * kCh + ch] = vmax;
+    __syncthreads();
+    if (tid < kCh) {
+      float m = red[tid];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k * kCh + tid]);
+      scale[tid] = m > 0.f ? m / 127.f : 1.f;
+    }
+    __syncthreads();
+
+    // ---- (3) quantise: item = (quad of 4 consecutive ox, channel); two words of 4 digits each
+    {
+      const float s = scale[ch], inv = 1.f / s;
+      for (int q = sub; q < kQuads; q += 8) {
+        const int oy = q / 5, ox0 = (q - oy * 5) * 4;
+        unsigned w1 = 0u, w2 = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int at = tile_pixel(oy, ox0 + k, blocked) * kCh + ch;
+          const float x = (so[at] > 0.f ? sg[at] : 0.f) * inv;
+          unsigned b1, b2;
+          const float q1 = round_magic(x, &b1);
+          const float r = fminf(fmaxf((x - q1) * 254.f, -127.f), 127.f);
+          round_magic(r, &b2);
+          w1 |= (b1 & 0xffu) << (8 * k);
+          w2 |= (b2 & 0xffu) << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(gq + ch * kGqPitch + 4 * q) = w1;
+        *reinterpret_cast<unsigned*>(gq + (kCh + ch) * kGqPitch + 4 * q) = w2;
+      }
+    }
+    __syncthreads();   // Zt and Gq complete; raw frame buffer `buf` and both tiles are consumed
+    if (tid == 0) {
+      if (f + 2 * stride < batch) load_frame(f + 2 * stride, buf);
+      if (f + stride < batch) load_tiles(f + stride);
+    }
+
+    // ---- (4) MMAs: acc[m][n][plane] over 13 k32 steps (8 quads each)
+    int acc[2][4][2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[m][n][p][k] = 0;
+
+#pragma unroll 1
+    for (int s = 0; s < kSteps; ++s) {
+      const int quad0 = 8 * s + t, quad1 = quad0 + 4;       // this lane's two quads of the step
+      unsigned a[2][2][4];                                   // [m-tile][plane][a0..a3]
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint8_t* row = gq + (p * kCh + 16 * m + g) * kGqPitch;
+          a[m][p][0] = *reinterpret_cast<const unsigned*>(row + 4 * quad0);
+          a[m][p][1] = *reinterpret_cast<const unsigned*>(row + 8 * kGqPitch + 4 * quad0);
+          a[m][p][2] = *reinterpret_cast<const unsigned*>(row + 4 * quad1);
+          a[m][p][3] = *reinterpret_cast<const unsigned*>(row + 8 * kGqPitch + 4 * quad1);
+        }
+      // byte offsets inside a tap plane of Zt of the two quads (clamped: padded quads have A = 0)
+      const int c0 = quad0 < kQuads ? quad0 : kQuads - 1, c1 = quad1 < kQuads ? quad1 : kQuads - 1;
+      const int off0 = (c0 / 5 + qa) * kZtRow + (c0 % 5) * 4 + qb;
+      const int off1 = (c1 / 5 + qa) * kZtRow + (c1 % 5) * 4 + qb;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const uint8_t* plane = zt + (tap0 + 8 * n + g) * kZtTap;
+        unsigned b0, b1;
+        if (qb == 0) {   // aligned
+          b0 = *reinterpret_cast<const unsigned*>(plane + off0);
+          b1 = *reinterpret_cast<const unsigned*>(plane + off1);
+        } else {         // bytes 1..4 of two aligned words
+          const unsigned* p0 = reinterpret_cast<const unsigned*>(plane + off0 - 1);
+          const unsigned* p1 = reinterpret_cast<const unsigned*>(plane + off1 - 1);
+          b0 = __byte_perm(p0[0], p0[1], 0x4321);
+          b1 = __byte_perm(p1[0], p1[1], 0x4321);
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_s8u8(acc[m][n][0], a[m][0], b0, b1);
+          mma_s8u8(acc[m][n][1], a[m][1], b0, b1);
+        }
+      }
+    }
+
+    // ---- (5) int32 -> fp32, apply the frame's per-channel scales
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float s_lo = scale[16 * m + g], s_hi = scale[16 * m + g + 8];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = (float)acc[m][n][0][k] + (float)acc[m][n][1][k] * (1.f / 254.f);
+          wsum[m][n][k] += v * (k < 2 ? s_lo : s_hi);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with Zt / Gq / scale before the next frame rewrites them
+  }
+
+  // ---- per-CTA partials: partial_w[cta][quadrant][tap][channel], partial_b[cta][channel]
+  float* pw = partial_w + (size_t)blockIdx.x * (4 * 64 * kCh) + (size_t)quadrant * (64 * kCh);
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int tap = tap0 + 8 * n + 2 * t, c_lo = 16 * m + g;
+      pw[tap * kCh + c_lo] = wsum[m][n][0];
+      pw[(tap + 1) * kCh + c_lo] = wsum[m][n][1];
+      pw[tap * kCh + c_lo + 8] = wsum[m][n][2];
+      pw[(tap + 1) * kCh + c_lo + 8] = wsum[m][n][3];
+    }
+  __syncthreads();
+  red[sub * kCh + ch] = bsum;
+  __syncthreads();
+  if (tid < kCh) {
+    float b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b += red[k * kCh + tid];
+    partial_b[(size_t)blockIdx.x * kCh + tid] = b;
+  }
+}
+
+// grad_w[n][c][4a+i][4b+j] = (1/255) * sum_cta partial_w[cta][a*2+b][(i*4+j)*4+c][n]
+__global__ void __launch_bounds__(256)
+stem_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restrict__ partial_b,
+                       int ctas, float* __restrict__ grad_w, float* __restrict__ grad_b) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over [32][4][8][8]
+  if (e < kCh * 256) {
+    const int kw = e & 7, kh = (e >> 3) & 7, c = (e >> 6) & 3, n = e >> 8;
+    const int quadrant = (kh >> 2) * 2 + (kw >> 2), tap = ((kh & 3) * 4 + (kw & 3)) * 4 + c;
+    const float* p = partial_w + ((size_t)quadrant * 64 + tap) * kCh + n;
+    double s = 0.0;
+    for (int b = 0; b < ctas; ++b) s += (double)__ldg(p + (size_t)b * (4 * 64 * kCh));
+    grad_w[e] = (float)(s * (1.0 / 255.0));
+  }
+  if (e < kCh) {
+    double s = 0.0;
+    for (int b = 0; b < ctas; ++b) s += (double)__ldg(partial_b + (size_t)b * kCh + e);
+    grad_b[e] = (float)s;
+  }
+}
+
+}  // namespace
+}  // namespace derl
+
+using namespace derl;
+
+extern "C" size_t derl_b200_stem_backward_workspace_bytes(void) {
+  return (size_t)sm_count() * (4 * 64 * kCh + kCh) * sizeof(float);
+}
+
+extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, const float* grad_out,
+                                       const float* out, int blocked, float* grad_weight,
+                                       float* grad_bias, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  DERL_REQUIRE(frames && grad_out && out && grad_weight && grad_bias && workspace && batch >= 1,
+               "stem_backward: bad arguments");
+  DERL_REQUIRE(blocked == 0 || blocked == 1, "stem_backward: blocked must be 0 or 1");
+  DERL_REQUIRE((((uintptr_t)frames | (uintptr_t)grad_out | (uintptr_t)out) & 15) == 0,
+               "stem_backward: inputs must be 16-byte aligned");
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  if (workspace_bytes < derl_b200_stem_backward_workspace_bytes()) {
+    set_error("stem_backward: workspace %zu B too small", workspace_bytes);
+    return DERL_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DERL_CUDA(cudaFuncSetAttribute(stem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)BwdSmem::bytes));
+    attr_set = true;
+  }
+  long long grid = batch < sm_count() ? batch : sm_count();
+  float* partial_w = reinterpret_cast<float*>(workspace);
+  float* partial_b = partial_w + (size_t)sm_count() * (4 * 64 * kCh);
+  stem_bwd_kernel<<<(unsigned)grid, kThreads, BwdSmem::bytes, st>>>(
+      frames, grad_out, out, partial_w, partial_b, batch, blocked);
+  DERL_LAUNCH_CHECK("stem_bwd_kernel");
+  stem_bwd_reduce_kernel<<<(kCh * 256 + 255) / 256, 256, 0, st>>>(partial_w, partial_b, (int)grid,
+                                                                  grad_weight, grad_bias);
+  DERL_LAUNCH_CHECK("stem_bwd_reduce_kernel");
+  return DERL_OK;
+}

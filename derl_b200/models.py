@@ -110,10 +110,16 @@ class _StemConvReLU(torch.autograd.Function):
     ctx.weight_dtype, ctx.out_block = weight.dtype, out_block
     return out
 
+  fused_backward = True   # K7: mask + bias grad + weight grad in one INT8 tensor-core kernel
+
   @staticmethod
   def backward(ctx, grad_out):
     frames, out = ctx.saved_tensors
     grad_out = grad_out.contiguous(memory_format=torch.channels_last)
+    if _StemConvReLU.fused_backward and out.dtype == torch.float32:
+      grad_w, grad_b = torch.ops.derl_b200.stem_backward(frames, grad_out, out,
+                                                         ctx.out_block == 2)
+      return None, grad_w.to(ctx.weight_dtype), grad_b, None, None
     # out_block 2: [B,128,10,10] with (i, j, c) channels; K5 stores the masked gradient
     # straight in the plain [B,32,20,20] layout the weight-gradient conv needs
     grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out, ctx.out_block)

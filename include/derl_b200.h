@@ -245,6 +245,23 @@ int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const flo
                              const float* bias_dev, void* out_dev, int out_dtype, int out_block,
                              void* stream);
 
+/* ------------------------------------------------------------------ K7: stem backward from uint8 frames
+ * Backward of the same layer (ReLU mask, bias gradient and weight gradient of
+ * nn.Conv2d(4, 32, 8, 4), derl/models.py:102-103) in one pass over the raw frames, the incoming
+ * gradient and the saved activation, on the INT8 tensor cores: the gradient is quantised per
+ * (frame, channel) into two signed 8-bit digit planes (block floating point, residual <= 1/508
+ * of the channel's largest element in that frame), frames are exact.
+ *   frames [batch, 84, 84, 4] uint8; grad_out, out: float32 [batch, 400, 32] tiles of the
+ *   activation gradient / activation, pixels in plain (oy*20 + ox) order (blocked = 0) or in the
+ *   space-to-depth(2) order K6 emits with out_block = 2 (blocked = 1);
+ *   grad_weight [32, 4, 8, 8] float32, grad_bias [32] float32 (overwritten).
+ *   workspace >= derl_b200_stem_backward_workspace_bytes().  Deterministic. */
+size_t derl_b200_stem_backward_workspace_bytes(void);
+int derl_b200_stem_backward(const uint8_t* frames_dev, int64_t batch, const float* grad_out_dev,
+                            const float* out_dev, int blocked, float* grad_weight_dev,
+                            float* grad_bias_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream);
+
 /* ------------------------------------------------------------------ K5: ReLU backward + bias grad
  * One pass over a channels-last activation gradient [rows, channels] (rows = B*H*W):
  *     grad_pre = out > 0 ? grad_out : 0;   bias_grad[c] = sum over rows of grad_pre[:, c]

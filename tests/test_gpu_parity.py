@@ -731,6 +731,38 @@ def test_stem_conv_kernel_vs_float32_convolution(dtype):
   torch.backends.cudnn.allow_tf32 = True
 
 
+@pytest.mark.parametrize("blocked", [False, True])
+def test_stem_backward_kernel_vs_float32_autograd(blocked):
+  """K7: ReLU mask + bias gradient + weight gradient from uint8 frames (INT8 MMA, gradient in
+  two 8-bit digit planes per frame and channel) against float32 autograd of the reference
+  formulation.  Tolerance 2e-3 of the largest gradient entry (TF32-class), bias 1e-5."""
+  torch.backends.cudnn.allow_tf32 = False
+  gen = torch.Generator(device=DEV).manual_seed(21)
+  weight = (torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.05).requires_grad_()
+  bias = (torch.randn(32, device=DEV, generator=gen) * 0.1).requires_grad_()
+  for batch in (1, 3, 310):
+    frames = torch.randint(0, 256, (batch, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
+    want_out = torch.relu(torch.nn.functional.conv2d(frames.permute(0, 3, 1, 2).float() / 255,
+                                                     weight, bias, stride=4))
+    grad = torch.randn(want_out.shape, device=DEV, generator=gen) * \
+        torch.rand(batch, 1, 1, 1, device=DEV, generator=gen) * 1e-3
+    weight.grad = bias.grad = None
+    want_out.backward(grad)
+    out = K.stem_conv_relu(frames, weight.detach(), bias.detach(), torch.float32, 2 if blocked else 1)
+    g_nhwc = grad.permute(0, 2, 3, 1).contiguous()
+    if blocked:
+      g_nhwc = K.space_to_depth(g_nhwc, 2, False)
+    grad_w, grad_b = K.stem_backward(frames, g_nhwc.permute(0, 3, 1, 2), out.permute(0, 3, 1, 2),
+                                     blocked)
+    assert grad_w.shape == (32, 4, 8, 8)
+    err_w = (grad_w - weight.grad).abs().max() / weight.grad.abs().max()
+    err_b = (grad_b - bias.grad).abs().max() / bias.grad.abs().max()
+    assert err_w < 2e-3 and err_b < 1e-4, (batch, float(err_w), float(err_b))
+    again = K.stem_backward(frames, g_nhwc.permute(0, 3, 1, 2), out.permute(0, 3, 1, 2), blocked)
+    assert torch.equal(again[0], grad_w) and torch.equal(again[1], grad_b)   # deterministic
+  torch.backends.cudnn.allow_tf32 = True
+
+
 def test_stem_autograd_matches_cudnn_path():
   """NatureCNN with the K6 stem (TF32 allowed) vs the cuDNN stem: outputs and all parameter
   gradients agree to TF32-level tolerance; the stem weight gradient lands in [32,4,8,8] layout."""
