@@ -735,30 +735,35 @@ def test_stem_conv_kernel_vs_float32_convolution(dtype):
 def test_stem_backward_kernel_vs_float32_autograd(blocked):
   """K7: ReLU mask + bias gradient + weight gradient from uint8 frames (INT8 MMA, gradient in
   two 8-bit digit planes per frame and channel) against float32 autograd of the reference
-  formulation.  Tolerance 2e-3 of the largest gradient entry (TF32-class), bias 1e-5."""
+  formulation evaluated with the SAME ReLU mask (the mask comes from the forward activation;
+  a reduced-precision forward may flip activations within ~1e-4 of zero, which is checked
+  separately): weight gradient within 2e-4 of its largest entry, bias within 1e-5."""
   torch.backends.cudnn.allow_tf32 = False
   gen = torch.Generator(device=DEV).manual_seed(21)
-  weight = (torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.05).requires_grad_()
-  bias = (torch.randn(32, device=DEV, generator=gen) * 0.1).requires_grad_()
+  weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.05
+  bias = torch.randn(32, device=DEV, generator=gen) * 0.1
   for batch in (1, 3, 310):
     frames = torch.randint(0, 256, (batch, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
-    want_out = torch.relu(torch.nn.functional.conv2d(frames.permute(0, 3, 1, 2).float() / 255,
-                                                     weight, bias, stride=4))
-    grad = torch.randn(want_out.shape, device=DEV, generator=gen) * \
+    inputs = frames.permute(0, 3, 1, 2).float() / 255
+    exact = torch.relu(torch.nn.functional.conv2d(inputs, weight, bias, stride=4))
+    out = K.stem_conv_relu(frames, weight, bias, torch.float32, 2 if blocked else 1)
+    plain = (K.space_to_depth(out, 2, True) if blocked else out).permute(0, 3, 1, 2)
+    assert int(((plain > 0) != (exact > 0)).sum()) <= max(2, exact.numel() // 20000)
+    grad = torch.randn(exact.shape, device=DEV, generator=gen) * \
         torch.rand(batch, 1, 1, 1, device=DEV, generator=gen) * 1e-3
-    weight.grad = bias.grad = None
-    want_out.backward(grad)
-    out = K.stem_conv_relu(frames, weight.detach(), bias.detach(), torch.float32, 2 if blocked else 1)
+    masked = grad * (plain > 0)
+    want_w = torch.nn.grad.conv2d_weight(inputs, weight.shape, masked, stride=4)
+    want_b = masked.sum((0, 2, 3))
     g_nhwc = grad.permute(0, 2, 3, 1).contiguous()
     if blocked:
       g_nhwc = K.space_to_depth(g_nhwc, 2, False)
-    grad_w, grad_b = K.stem_backward(frames, g_nhwc.permute(0, 3, 1, 2), out.permute(0, 3, 1, 2),
-                                     blocked)
+    args = (frames, g_nhwc.permute(0, 3, 1, 2), out.permute(0, 3, 1, 2), blocked)
+    grad_w, grad_b = K.stem_backward(*args)
     assert grad_w.shape == (32, 4, 8, 8)
-    err_w = (grad_w - weight.grad).abs().max() / weight.grad.abs().max()
-    err_b = (grad_b - bias.grad).abs().max() / bias.grad.abs().max()
-    assert err_w < 2e-3 and err_b < 1e-4, (batch, float(err_w), float(err_b))
-    again = K.stem_backward(frames, g_nhwc.permute(0, 3, 1, 2), out.permute(0, 3, 1, 2), blocked)
+    err_w = (grad_w - want_w).abs().max() / want_w.abs().max()
+    err_b = (grad_b - want_b).abs().max() / want_b.abs().max()
+    assert err_w < 2e-4 and err_b < 1e-5, (batch, float(err_w), float(err_b))
+    again = K.stem_backward(*args)
     assert torch.equal(again[0], grad_w) and torch.equal(again[1], grad_b)   # deterministic
   torch.backends.cudnn.allow_tf32 = True
 
