@@ -87,6 +87,11 @@ def main():
     timed(f"stem_conv_relu 32768 f32 blk{blk}",
           lambda: K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, blk),
           32768 * (28224 + 400 * 32 * 4.0))
+  act = K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, 2).permute(0, 3, 1, 2)
+  gact = torch.randn_like(act) * 1e-3
+  timed("stem_backward 32768 blocked", lambda: K.stem_backward(obs[:32768], gact, act, True),
+        32768 * (28224 + 2 * 51200.0))
+  del act, gact
   frames = obs[:16384]
   for dt, nb in ((torch.float32, 5.0), (torch.bfloat16, 3.0)):
     timed(f"frames_to_s2d 16384 {str(dt)[6:]}", lambda: K.frames_to_s2d(frames, 4, dt, 255.0),
