@@ -17,7 +17,7 @@
 //   Gq[plane][channel][pixel] (written by the quantiser) and Zt[tap][Y][X], a byte transpose of
 //   the space-to-depth(4) frame (4x4 byte blocks, PRMT), in which 4 consecutive output pixels of
 //   one row are 4 consecutive bytes.
-//   One CTA (8 warps) per SM loops over frames; warp w owns quadrant w/2 and 32 of its taps.
+//   One CTA (16 warps) per SM loops over frames; warp w owns quadrant w/4 and 16 of its taps.
 //   Inputs arrive by TMA bulk copies; the next frame's copies are in flight during the MMAs.
 // Per-CTA partial sums are reduced (fixed order) and re-indexed to [32, 4, 8, 8] by a second
 // small kernel.
@@ -31,19 +31,30 @@ constexpr int kPix = 400, kCh = 32;           // output pixels, output channels
 constexpr int kTileBytes = kPix * kCh * 4;    // 51200: one frame's [400 x 32] float32 tile
 constexpr int kQuads = 100;                   // 4 consecutive ox of one oy
 constexpr int kSteps = 13;                    // ceil(100 quads / 8 quads per k32 step)
-constexpr int kGqPitch = 420;                 // bytes per (plane, channel) row: 105 words (odd)
-constexpr int kZtRow = 24, kZtTap = 21 * kZtRow;   // Zt[tap][Y (21)][X (24, 21 used)]
-constexpr int kWarps = 8, kThreads = kWarps * 32;
+constexpr int kGroups = 26;                   // groups of 4 quads (16 pixels); the 26th is zero padding
+constexpr int kGqPlane = kGroups * kCh * 16;  // Gq[plane][group][channel][4 quads x 4 digits]
+// Zt[plane][Y (21)][X (24, 21 used)], plane = c * 16 + (i * 4 + j).  A pitch of 130 words puts plane k
+// at bank 2k: the transpose's stores (16 (i, j) x 2 X-blocks per warp) and the MMA's B loads (8 planes
+// of equal c and equal (i, j) parity x 4 words) both touch every bank once.
+constexpr int kZtRow = 24, kZtTap = 520;
+#ifndef DERL_STEM_BWD_WARPS
+#define DERL_STEM_BWD_WARPS 8
+#endif
+constexpr int kWarps = DERL_STEM_BWD_WARPS, kThreads = kWarps * 32;
+constexpr int kWarpsPerQuadrant = kWarps / 4;   // warps sharing one kernel quadrant (a, b)
+constexpr int kNT = 8 / kWarpsPerQuadrant;      // n8 tap tiles per warp
 
 struct BwdSmem {
   static constexpr size_t frame_off = 0;                              // [2][28224] u8
   static constexpr size_t grad_off = frame_off + 2 * (size_t)kFrameBytes + 64;   // float [400][32]
   static constexpr size_t out_off = grad_off + kTileBytes;            // float [400][32]
-  static constexpr size_t zt_off = out_off + kTileBytes;              // u8 [64][504]
-  static constexpr size_t gq_off = zt_off + 64 * (size_t)kZtTap;      // s8 [2][32][420]
-  static constexpr size_t red_off = gq_off + 2 * kCh * (size_t)kGqPitch;  // float [8][32]
-  static constexpr size_t scale_off = red_off + 8 * kCh * 4;          // float [32]
-  static constexpr size_t bar_off = scale_off + kCh * 4;              // 3 mbarriers
+  static constexpr size_t zt_off = out_off + kTileBytes;              // u8 [64][520]
+  static constexpr size_t gq_off = zt_off + 64 * (size_t)kZtTap;      // s8 [2][26][32][16]
+  static constexpr size_t red_off = gq_off + 2 * (size_t)kGqPlane;  // float [kWarps][32]
+  static constexpr size_t scale_off = red_off + kWarps * kCh * 4;     // float [32]
+  static constexpr size_t qtile_off = scale_off + kCh * 4;            // int [104]: quad -> tile offset
+  static constexpr size_t qzt_off = qtile_off + 104 * 4;              // int [104]: quad -> Zt offset
+  static constexpr size_t bar_off = qzt_off + 104 * 4;                // 3 mbarriers
   static constexpr size_t bytes = bar_off + 32;
 };
 
@@ -82,6 +93,8 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
   uint8_t* gq = smem + BwdSmem::gq_off;
   float* red = reinterpret_cast<float*>(smem + BwdSmem::red_off);
   float* scale = reinterpret_cast<float*>(smem + BwdSmem::scale_off);
+  int* qtile = reinterpret_cast<int*>(smem + BwdSmem::qtile_off);
+  int* qzt = reinterpret_cast<int*>(smem + BwdSmem::qzt_off);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar_off);  // [0,1] frames, [2] tiles
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -109,23 +122,33 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     }
     if (first + stride < batch) load_frame(first + stride, 1);
   }
-  // zero the quantised-gradient buffer once: its padding (quads 100..104) must stay zero
-  for (int i = tid; i < 2 * kCh * kGqPitch / 4; i += kThreads) {
+  // zero the quantised-gradient buffer once: its padding (quads 100..103) must stay zero
+  for (int i = tid; i < 2 * kGqPlane / 4; i += kThreads) {
     reinterpret_cast<unsigned*>(gq)[i] = 0u;
   }
+  // quad q = 4 consecutive ox of row oy = q / 5: float offset of its first pixel inside a tile,
+  // byte offset of its first pixel inside a Zt tap plane (quads >= 100 are padding: A is zero)
+  if (tid < 104) {
+    const int q = tid < kQuads ? tid : kQuads - 1;
+    const int oy = q / 5, ox0 = (q - oy * 5) * 4;
+    qtile[tid] = tile_pixel(oy, ox0, blocked) * kCh;
+    qzt[tid] = oy * kZtRow + ox0;
+  }
+  // float offsets of the quad's 4 pixels relative to its first one
+  const int step1 = kCh, step2 = (blocked ? 4 : 2) * kCh, step3 = (blocked ? 5 : 3) * kCh;
   __syncthreads();
 
   // ---- loop-invariant roles
-  const int quadrant = warp >> 1;                 // (a, b) = (quadrant >> 1, quadrant & 1)
+  const int quadrant = warp / kWarpsPerQuadrant;  // (a, b) = (quadrant >> 1, quadrant & 1)
   const int qa = quadrant >> 1, qb = quadrant & 1;
-  const int tap0 = (warp & 1) * 32;               // this warp's 32 taps: tap0 + 8*nt + g
-  const int ch = tid & 31, sub = tid >> 5;        // quantiser role: channel, pixel subset (8)
+  const int ntile0 = (warp % kWarpsPerQuadrant) * kNT;   // n-tile nt: channel nt >> 1, (i,j) parity nt & 1
+  const int ch = tid & 31, sub = tid >> 5;        // quantiser role: channel, pixel subset
 
-  float wsum[2][4][4];                            // [m-tile][n-tile][c-frag] fp32 running sums
+  float wsum[2][kNT][4];                           // [m-tile][n-tile][c-frag] fp32 running sums
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
+    for (int n = 0; n < kNT; ++n)
 #pragma unroll
       for (int k = 0; k < 4; ++k) wsum[m][n][k] = 0.f;
   float bsum = 0.f;
@@ -137,12 +160,13 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     mbar_wait(&bar[buf], (unsigned)((it >> 1) & 1));
     mbar_wait(&bar[2], (unsigned)(it & 1));
 
-    // ---- (1) byte transpose of the frame: Zt[(i*4+j)*4+c][Y][X] = raw[4Y+i][4X+j][c]
+    // ---- (1) byte transpose of the frame: Zt[c*16+i*4+j][Y][X] = raw[4Y+i][4X+j][c]
     // one 4x4 byte block per step: 4 source words (X..X+3, channels c=0..3 each) ->
     // 4 destination words (taps c=0..3, bytes X..X+3)
-    for (int blk = tid; blk < 21 * 16 * 6; blk += kThreads) {
-      const int xg = blk % 6, ij = (blk / 6) & 15, Y = blk / 96;
-      const int i = ij >> 2, j = ij & 3;
+    // lane = j + 4*(xg & 1) + 8*i makes the 32 source words of a warp hit 32 distinct banks
+    for (int blk = warp; blk < 21 * 3; blk += kWarps) {
+      const int Y = blk / 3, xg = (blk - Y * 3) * 2 + ((lane >> 2) & 1);
+      const int i = lane >> 3, j = lane & 3, ij = i * 4 + j;
       const uint8_t* src = raw + (4 * Y + i) * 336 + (16 * xg + j) * 4;
       unsigned w0 = *reinterpret_cast<const unsigned*>(src);
       unsigned w1 = *reinterpret_cast<const unsigned*>(src + 16);
@@ -153,17 +177,19 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
       const unsigned t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
       const unsigned c0 = __byte_perm(t0, t2, 0x5410), c1 = __byte_perm(t0, t2, 0x7632);
       const unsigned c2 = __byte_perm(t1, t3, 0x5410), c3 = __byte_perm(t1, t3, 0x7632);
-      uint8_t* dst = zt + (ij * 4) * kZtTap + Y * kZtRow + 4 * xg;
+      uint8_t* dst = zt + ij * kZtTap + Y * kZtRow + 4 * xg;
       *reinterpret_cast<unsigned*>(dst) = c0;
-      *reinterpret_cast<unsigned*>(dst + kZtTap) = c1;
-      *reinterpret_cast<unsigned*>(dst + 2 * kZtTap) = c2;
-      *reinterpret_cast<unsigned*>(dst + 3 * kZtTap) = c3;
+      *reinterpret_cast<unsigned*>(dst + 16 * kZtTap) = c1;
+      *reinterpret_cast<unsigned*>(dst + 32 * kZtTap) = c2;
+      *reinterpret_cast<unsigned*>(dst + 48 * kZtTap) = c3;
     }
 
-    // ---- (2) ReLU mask, per-channel max and bias sum: thread = (channel, one of 8 pixel subsets)
+    // ---- (2) ReLU mask, per-channel max and bias sum: thread = (channel, one of kWarps pixel subsets)
     float vmax = 0.f, vsum = 0.f;
-    for (int p = sub; p < kPix; p += 8) {
+#pragma unroll 5
+    for (int p = sub; p < kPix; p += kWarps) {
       const float gv = so[p * kCh + ch] > 0.f ? sg[p * kCh + ch] : 0.f;
+      sg[p * kCh + ch] = gv;   // masked in place: the quantiser below reads only this tile
       vmax = fmaxf(vmax, fabsf(gv));
       vsum += gv;
     }
@@ -173,32 +199,39 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     if (tid < kCh) {
       float m = red[tid];
 #pragma unroll
-      for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k * kCh + tid]);
+      for (int k = 1; k < kWarps; ++k) m = fmaxf(m, red[k * kCh + tid]);
       scale[tid] = m > 0.f ? m / 127.f : 1.f;
     }
     __syncthreads();
 
-    // ---- (3) quantise: item = (quad of 4 consecutive ox, channel); two words of 4 digits each
+    // ---- (3) quantise: item = (group of 4 quads, channel); one 16-byte store per digit plane
     {
       const float s = scale[ch], inv = 1.f / s;
-      for (int q = sub; q < kQuads; q += 8) {
-        const int oy = q / 5, ox0 = (q - oy * 5) * 4;
-        unsigned w1 = 0u, w2 = 0u;
+      for (int grp = sub; grp < kQuads / 4; grp += kWarps) {
+        unsigned w1[4], w2[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int at = tile_pixel(oy, ox0 + k, blocked) * kCh + ch;
-          const float x = (so[at] > 0.f ? sg[at] : 0.f) * inv;
-          unsigned b1, b2;
-          const float q1 = round_magic(x, &b1);
-          const float r = fminf(fmaxf((x - q1) * 254.f, -127.f), 127.f);
-          round_magic(r, &b2);
-          w1 |= (b1 & 0xffu) << (8 * k);
-          w2 |= (b2 & 0xffu) << (8 * k);
+        for (int qq = 0; qq < 4; ++qq) {
+          const float* px = sg + qtile[4 * grp + qq] + ch;
+          const float v[4] = {px[0], px[step1], px[step2], px[step3]};
+          w1[qq] = 0u;
+          w2[qq] = 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x = v[k] * inv;
+            unsigned b1, b2;
+            const float q1 = round_magic(x, &b1);
+            const float r = fminf(fmaxf((x - q1) * 254.f, -127.f), 127.f);
+            round_magic(r, &b2);
+            w1[qq] |= (b1 & 0xffu) << (8 * k);
+            w2[qq] |= (b2 & 0xffu) << (8 * k);
+          }
         }
-        *reinterpret_cast<unsigned*>(gq + ch * kGqPitch + 4 * q) = w1;
-        *reinterpret_cast<unsigned*>(gq + (kCh + ch) * kGqPitch + 4 * q) = w2;
+        uint8_t* at = gq + (grp * kCh + ch) * 16;
+        *reinterpret_cast<uint4*>(at) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        *reinterpret_cast<uint4*>(at + kGqPlane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
       }
     }
+    fence_proxy_async_smem();   // the in-place masking wrote the tile the next bulk copy overwrites
     __syncthreads();   // Zt and Gq complete; raw frame buffer `buf` and both tiles are consumed
     if (tid == 0) {
       if (f + 2 * stride < batch) load_frame(f + 2 * stride, buf);
@@ -206,11 +239,11 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     }
 
     // ---- (4) MMAs: acc[m][n][plane] over 13 k32 steps (8 quads each)
-    int acc[2][4][2][4];
+    int acc[2][kNT][2][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int n = 0; n < 4; ++n)
+      for (int n = 0; n < kNT; ++n)
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -224,19 +257,19 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-          const uint8_t* row = gq + (p * kCh + 16 * m + g) * kGqPitch;
-          a[m][p][0] = *reinterpret_cast<const unsigned*>(row + 4 * quad0);
-          a[m][p][1] = *reinterpret_cast<const unsigned*>(row + 8 * kGqPitch + 4 * quad0);
-          a[m][p][2] = *reinterpret_cast<const unsigned*>(row + 4 * quad1);
-          a[m][p][3] = *reinterpret_cast<const unsigned*>(row + 8 * kGqPitch + 4 * quad1);
+          // quads 8s + t and 8s + 4 + t live in groups 2s and 2s + 1 at word t
+          const uint8_t* row = gq + p * kGqPlane + ((2 * s) * kCh + 16 * m + g) * 16 + 4 * t;
+          a[m][p][0] = *reinterpret_cast<const unsigned*>(row);
+          a[m][p][1] = *reinterpret_cast<const unsigned*>(row + 8 * 16);
+          a[m][p][2] = *reinterpret_cast<const unsigned*>(row + kCh * 16);
+          a[m][p][3] = *reinterpret_cast<const unsigned*>(row + (kCh + 8) * 16);
         }
-      // byte offsets inside a tap plane of Zt of the two quads (clamped: padded quads have A = 0)
-      const int c0 = quad0 < kQuads ? quad0 : kQuads - 1, c1 = quad1 < kQuads ? quad1 : kQuads - 1;
-      const int off0 = (c0 / 5 + qa) * kZtRow + (c0 % 5) * 4 + qb;
-      const int off1 = (c1 / 5 + qa) * kZtRow + (c1 % 5) * 4 + qb;
+      // byte offsets of the two quads inside a Zt tap plane, shifted by this warp's quadrant
+      const int off0 = qzt[quad0] + qa * kZtRow + qb, off1 = qzt[quad1] + qa * kZtRow + qb;
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const uint8_t* plane = zt + (tap0 + 8 * n + g) * kZtTap;
+      for (int n = 0; n < kNT; ++n) {
+        const int nt = ntile0 + n;
+        const uint8_t* plane = zt + ((nt >> 1) * 16 + 2 * g + (nt & 1)) * kZtTap;
         unsigned b0, b1;
         if (qb == 0) {   // aligned
           b0 = *reinterpret_cast<const unsigned*>(plane + off0);
@@ -260,7 +293,7 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     for (int m = 0; m < 2; ++m) {
       const float s_lo = scale[16 * m + g], s_hi = scale[16 * m + g + 8];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
+      for (int n = 0; n < kNT; ++n) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float v = (float)acc[m][n][0][k] + (float)acc[m][n][1][k] * (1.f / 254.f);
@@ -276,12 +309,14 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const int tap = tap0 + 8 * n + 2 * t, c_lo = 16 * m + g;
+    for (int n = 0; n < kNT; ++n) {
+      // D column col (= 2t, 2t + 1) of n-tile nt is (i, j) = 2 col + (nt & 1), channel nt >> 1
+      const int nt = ntile0 + n, c_lo = 16 * m + g;
+      const int tap = ((4 * t + (nt & 1)) << 2) + (nt >> 1);   // (i*4+j)*4 + c of column 2t
       pw[tap * kCh + c_lo] = wsum[m][n][0];
-      pw[(tap + 1) * kCh + c_lo] = wsum[m][n][1];
+      pw[(tap + 8) * kCh + c_lo] = wsum[m][n][1];
       pw[tap * kCh + c_lo + 8] = wsum[m][n][2];
-      pw[(tap + 1) * kCh + c_lo + 8] = wsum[m][n][3];
+      pw[(tap + 8) * kCh + c_lo + 8] = wsum[m][n][3];
     }
   __syncthreads();
   red[sub * kCh + ch] = bsum;
@@ -289,7 +324,7 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
   if (tid < kCh) {
     float b = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) b += red[k * kCh + tid];
+    for (int k = 0; k < kWarps; ++k) b += red[k * kCh + tid];
     partial_b[(size_t)blockIdx.x * kCh + tid] = b;
   }
 }
