@@ -14,11 +14,15 @@
 //   GEMM view per frame and per kernel quadrant (a, b):  D[32 ch x 64 taps] += Gq^T [32 x 400]
 //   * Z_ab [400 x 64], reduction over the output pixels.  MMA packs 4 consecutive reduction
 //   indices per register, so both operands are laid out pixel-fastest in shared memory:
-//   Gq[plane][channel][pixel] (written by the quantiser) and Zt[tap][Y][X], a byte transpose of
-//   the space-to-depth(4) frame (4x4 byte blocks, PRMT), in which 4 consecutive output pixels of
-//   one row are 4 consecutive bytes.
-//   One CTA (16 warps) per SM loops over frames; warp w owns quadrant w/4 and 16 of its taps.
-//   Inputs arrive by TMA bulk copies; the next frame's copies are in flight during the MMAs.
+//   Gq[plane][group of 16 pixels][channel][16 digits] (written by the quantiser) and
+//   Zt[c*16 + i*4 + j][Y][X], a byte transpose of the space-to-depth(4) frame (4x4 byte blocks,
+//   PRMT), in which 4 consecutive output pixels of one row are 4 consecutive bytes.  Both layouts
+//   are bank-conflict free for their writer and for the MMA fragment loads.
+//   Two CTAs (8 warps each) per SM loop over frames; each CTA runs its phases (transpose,
+//   mask + quantise, MMA) back to back and the SM overlaps one CTA's ALU phases with the other's
+//   tensor phase.  The frame arrives by a TMA bulk copy; the gradient and activation tiles are
+//   read with coalesced streaming loads straight into registers (one channel per lane), issued
+//   before the transpose so that they land while it runs.  Warp w owns quadrant w/2 and 32 taps.
 // Per-CTA partial sums are reduced (fixed order) and re-indexed to [32, 4, 8, 8] by a second
 // small kernel.
 #include "common.cuh"
@@ -28,8 +32,7 @@ namespace {
 
 constexpr int kFrameBytes = 84 * 84 * 4;      // 28224
 constexpr int kPix = 400, kCh = 32;           // output pixels, output channels
-constexpr int kTileBytes = kPix * kCh * 4;    // 51200: one frame's [400 x 32] float32 tile
-constexpr int kQuads = 100;                   // 4 consecutive ox of one oy
+constexpr int kQuads = 100;                   // 4 consecutive ox of one oy (order: see the tables)
 constexpr int kSteps = 13;                    // ceil(100 quads / 8 quads per k32 step)
 constexpr int kGroups = 26;                   // groups of 4 quads (16 pixels); the 26th is zero padding
 constexpr int kGqPlane = kGroups * kCh * 16;  // Gq[plane][group][channel][4 quads x 4 digits]
@@ -37,26 +40,23 @@ constexpr int kGqPlane = kGroups * kCh * 16;  // Gq[plane][group][channel][4 qua
 // at bank 2k: the transpose's stores (16 (i, j) x 2 X-blocks per warp) and the MMA's B loads (8 planes
 // of equal c and equal (i, j) parity x 4 words) both touch every bank once.
 constexpr int kZtRow = 24, kZtTap = 520;
-#ifndef DERL_STEM_BWD_WARPS
-#define DERL_STEM_BWD_WARPS 8
-#endif
-constexpr int kWarps = DERL_STEM_BWD_WARPS, kThreads = kWarps * 32;
-constexpr int kWarpsPerQuadrant = kWarps / 4;   // warps sharing one kernel quadrant (a, b)
-constexpr int kNT = 8 / kWarpsPerQuadrant;      // n8 tap tiles per warp
+constexpr int kWarps = 8, kThreads = kWarps * 32, kCtasPerSm = 2;
+constexpr int kNT = 4;                        // n8 tap tiles per warp (2 warps per quadrant)
+constexpr int kPartial = 4 * 64 * kCh;        // floats of one CTA's weight partial
 
 struct BwdSmem {
-  static constexpr size_t frame_off = 0;                              // [2][28224] u8
-  static constexpr size_t grad_off = frame_off + 2 * (size_t)kFrameBytes + 64;   // float [400][32]
-  static constexpr size_t out_off = grad_off + kTileBytes;            // float [400][32]
-  static constexpr size_t zt_off = out_off + kTileBytes;              // u8 [64][520]
+  static constexpr size_t frame_off = 0;                              // [28224] u8 (+64: the
+  static constexpr size_t zt_off = frame_off + kFrameBytes + 64;      //  transpose over-reads)
   static constexpr size_t gq_off = zt_off + 64 * (size_t)kZtTap;      // s8 [2][26][32][16]
-  static constexpr size_t red_off = gq_off + 2 * (size_t)kGqPlane;  // float [kWarps][32]
+  static constexpr size_t red_off = gq_off + 2 * (size_t)kGqPlane;    // float [kWarps][32]
   static constexpr size_t scale_off = red_off + kWarps * kCh * 4;     // float [32]
   static constexpr size_t qtile_off = scale_off + kCh * 4;            // int [104]: quad -> tile offset
   static constexpr size_t qzt_off = qtile_off + 104 * 4;              // int [104]: quad -> Zt offset
-  static constexpr size_t bar_off = qzt_off + 104 * 4;                // 3 mbarriers
-  static constexpr size_t bytes = bar_off + 32;
+  static constexpr size_t bar_off = qzt_off + 104 * 4;                // 1 mbarrier
+  static constexpr size_t bytes = bar_off + 16;
 };
+static_assert(BwdSmem::zt_off % 16 == 0 && BwdSmem::gq_off % 16 == 0, "smem alignment");
+static_assert(kCtasPerSm * (BwdSmem::bytes + 1024) <= 228 * 1024, "two CTAs must fit one SM");
 
 __device__ __forceinline__ void mma_s8u8(int (&d)[4], const unsigned (&a)[4], unsigned b0,
                                          unsigned b1) {
@@ -73,78 +73,79 @@ __device__ __forceinline__ int tile_pixel(int oy, int ox, int blocked) {
   return oy * 20 + ox;
 }
 
-// rint(x) for |x| < 2^22 and its two's-complement low byte, without the conversion pipe
-__device__ __forceinline__ float round_magic(float x, unsigned* bits) {
-  const float m = x + 12582912.f;   // 1.5 * 2^23
-  *bits = __float_as_uint(m);
-  return m - 12582912.f;
+// Two-digit quantisation of x in [-127, 127]: q1 = rint(x), q2 = rint((x - q1) * 254) (|q2| <= 127
+// because |x - q1| <= 1/2 exactly).  Rounding by the 1.5 * 2^23 trick keeps the conversion pipe
+// idle; the digits are the low bytes of the biased sums.
+__device__ __forceinline__ void quantise(float x, unsigned* b1, unsigned* b2) {
+  const float m1 = x + 12582912.f;
+  *b1 = __float_as_uint(m1);
+  const float r = (x - (m1 - 12582912.f)) * 254.f;
+  *b2 = __float_as_uint(r + 12582912.f);
+}
+
+// low bytes of four words -> one word
+__device__ __forceinline__ unsigned pack4(unsigned a, unsigned b, unsigned c, unsigned d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
 // grad_out / out: [B, 400, 32] float32 tiles (plain pixel order, or space-to-depth(2) order when
 // blocked != 0); partial_w: [grid][4 quadrants][64 taps][32 ch]; partial_b: [grid][32].
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ grad_out,
                 const float* __restrict__ out, float* __restrict__ partial_w,
                 float* __restrict__ partial_b, long long batch, int blocked) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float* sg = reinterpret_cast<float*>(smem + BwdSmem::grad_off);
-  float* so = reinterpret_cast<float*>(smem + BwdSmem::out_off);
+  uint8_t* raw = smem + BwdSmem::frame_off;
   uint8_t* zt = smem + BwdSmem::zt_off;
   uint8_t* gq = smem + BwdSmem::gq_off;
   float* red = reinterpret_cast<float*>(smem + BwdSmem::red_off);
   float* scale = reinterpret_cast<float*>(smem + BwdSmem::scale_off);
   int* qtile = reinterpret_cast<int*>(smem + BwdSmem::qtile_off);
   int* qzt = reinterpret_cast<int*>(smem + BwdSmem::qzt_off);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar_off);  // [0,1] frames, [2] tiles
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const long long first = blockIdx.x, stride = gridDim.x;
 
-  auto load_frame = [&](long long f, int buf) {
-    mbar_expect_tx(&bar[buf], kFrameBytes);
-    bulk_g2s(smem + BwdSmem::frame_off + (size_t)buf * kFrameBytes, frames + f * kFrameBytes,
-             kFrameBytes, &bar[buf]);
-  };
-  auto load_tiles = [&](long long f) {
-    mbar_expect_tx(&bar[2], 2 * kTileBytes);
-    bulk_g2s(sg, grad_out + f * (kPix * kCh), kTileBytes, &bar[2]);
-    bulk_g2s(so, out + f * (kPix * kCh), kTileBytes, &bar[2]);
+  auto load_frame = [&](long long f) {
+    mbar_expect_tx(bar, kFrameBytes);
+    bulk_g2s(raw, frames + f * kFrameBytes, kFrameBytes, bar);
   };
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_init(&bar[2], 1);
+    mbar_init(bar, 1);
     mbar_fence_init();
-    if (first < batch) {
-      load_frame(first, 0);
-      load_tiles(first);
-    }
-    if (first + stride < batch) load_frame(first + stride, 1);
+    if (first < batch) load_frame(first);
   }
   // zero the quantised-gradient buffer once: its padding (quads 100..103) must stay zero
   for (int i = tid; i < 2 * kGqPlane / 4; i += kThreads) {
     reinterpret_cast<unsigned*>(gq)[i] = 0u;
   }
-  // quad q = 4 consecutive ox of row oy = q / 5: float offset of its first pixel inside a tile,
-  // byte offset of its first pixel inside a Zt tap plane (quads >= 100 are padding: A is zero)
+  // quad q = 4 consecutive ox of one row.  The reduction order is ours to choose: quads 0..79 are
+  // (oy = q / 4, ox0 = 4 (q % 4)), quads 80..99 the fifth quad (ox0 = 16) of row q - 80, so that the
+  // 4 quads one B-fragment load touches (4 consecutive q) are 4 consecutive words of one Zt row.
+  // Tables: float offset of the quad's first pixel inside a tile, byte offset inside a Zt plane
+  // (quads >= 100 are padding: A is zero there)
   if (tid < 104) {
     const int q = tid < kQuads ? tid : kQuads - 1;
-    const int oy = q / 5, ox0 = (q - oy * 5) * 4;
+    const int oy = q < 80 ? q >> 2 : q - 80, ox0 = q < 80 ? (q & 3) * 4 : 16;
     qtile[tid] = tile_pixel(oy, ox0, blocked) * kCh;
     qzt[tid] = oy * kZtRow + ox0;
   }
-  // float offsets of the quad's 4 pixels relative to its first one
-  const int step1 = kCh, step2 = (blocked ? 4 : 2) * kCh, step3 = (blocked ? 5 : 3) * kCh;
+  // float offsets of a quad's 4 pixels relative to its first one
+  const int step[4] = {0, kCh, (blocked ? 4 : 2) * kCh, (blocked ? 5 : 3) * kCh};
   __syncthreads();
 
   // ---- loop-invariant roles
-  const int quadrant = warp / kWarpsPerQuadrant;  // (a, b) = (quadrant >> 1, quadrant & 1)
+  const int quadrant = warp >> 1;                 // (a, b) = (quadrant >> 1, quadrant & 1)
   const int qa = quadrant >> 1, qb = quadrant & 1;
-  const int ntile0 = (warp % kWarpsPerQuadrant) * kNT;   // n-tile nt: channel nt >> 1, (i,j) parity nt & 1
-  const int ch = tid & 31, sub = tid >> 5;        // quantiser role: channel, pixel subset
+  const int ntile0 = (warp & 1) * kNT;            // n-tile nt: channel nt >> 1, (i, j) parity nt & 1
+  // mask / quantiser role: lane = channel; warp `sub` owns groups sub, sub + 8, sub + 16 (12 quads)
+  // and, for sub < 4, quad 96 + sub of the last group
+  const int ch = lane, sub = warp;
+  const bool extra = sub < 4;
 
-  float wsum[2][kNT][4];                           // [m-tile][n-tile][c-frag] fp32 running sums
+  float wsum[2][kNT][4];                          // [m-tile][n-tile][c-frag] fp32 running sums
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -155,15 +156,30 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 
   int it = 0;
   for (long long f = first; f < batch; f += stride, ++it) {
-    const int buf = it & 1;
-    const uint8_t* raw = smem + BwdSmem::frame_off + (size_t)buf * kFrameBytes;
-    mbar_wait(&bar[buf], (unsigned)((it >> 1) & 1));
-    mbar_wait(&bar[2], (unsigned)(it & 1));
+    const float* gt = grad_out + f * (kPix * kCh) + ch;
+    const float* ot = out + f * (kPix * kCh) + ch;
+
+    // ---- (0) issue this thread's gradient loads (each warp-load is one pixel: 128 contiguous B)
+    float v[3][16], vx[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float* px = gt + qtile[4 * (sub + 8 * k) + qq];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[k][4 * qq + e] = __ldcs(px + step[e]);
+      }
+    {
+      const float* px = gt + qtile[96 + (sub & 3)];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) vx[e] = extra ? __ldcs(px + step[e]) : 0.f;
+    }
 
     // ---- (1) byte transpose of the frame: Zt[c*16+i*4+j][Y][X] = raw[4Y+i][4X+j][c]
-    // one 4x4 byte block per step: 4 source words (X..X+3, channels c=0..3 each) ->
-    // 4 destination words (taps c=0..3, bytes X..X+3)
+    // one 4x4 byte block per lane and step: 4 source words (X..X+3, channels c=0..3 each) ->
+    // 4 destination words (planes c=0..3, bytes X..X+3).
     // lane = j + 4*(xg & 1) + 8*i makes the 32 source words of a warp hit 32 distinct banks
+    mbar_wait(bar, (unsigned)(it & 1));
     for (int blk = warp; blk < 21 * 3; blk += kWarps) {
       const int Y = blk / 3, xg = (blk - Y * 3) * 2 + ((lane >> 2) & 1);
       const int i = lane >> 3, j = lane & 3, ij = i * 4 + j;
@@ -184,59 +200,68 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
       *reinterpret_cast<unsigned*>(dst + 48 * kZtTap) = c3;
     }
 
-    // ---- (2) ReLU mask, per-channel max and bias sum: thread = (channel, one of kWarps pixel subsets)
+    // ---- (2) ReLU mask, per-channel max and bias sum, values stay in registers
     float vmax = 0.f, vsum = 0.f;
-#pragma unroll 5
-    for (int p = sub; p < kPix; p += kWarps) {
-      const float gv = so[p * kCh + ch] > 0.f ? sg[p * kCh + ch] : 0.f;
-      sg[p * kCh + ch] = gv;   // masked in place: the quantiser below reads only this tile
-      vmax = fmaxf(vmax, fabsf(gv));
-      vsum += gv;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float* px = ot + qtile[4 * (sub + 8 * k) + qq];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float gv = __ldcs(px + step[e]) > 0.f ? v[k][4 * qq + e] : 0.f;
+          v[k][4 * qq + e] = gv;
+          vmax = fmaxf(vmax, fabsf(gv));
+          vsum += gv;
+        }
+      }
+    if (extra) {
+      const float* px = ot + qtile[96 + sub];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gv = __ldcs(px + step[e]) > 0.f ? vx[e] : 0.f;
+        vx[e] = gv;
+        vmax = fmaxf(vmax, fabsf(gv));
+        vsum += gv;
+      }
     }
     bsum += vsum;
     red[sub * kCh + ch] = vmax;
-    __syncthreads();
-    if (tid < kCh) {
-      float m = red[tid];
-#pragma unroll
-      for (int k = 1; k < kWarps; ++k) m = fmaxf(m, red[k * kCh + tid]);
-      scale[tid] = m > 0.f ? m / 127.f : 1.f;
-    }
-    __syncthreads();
+    __syncthreads();   // maxima published; every warp is done with the raw frame
+    if (tid == 0 && f + stride < batch) load_frame(f + stride);
 
-    // ---- (3) quantise: item = (group of 4 quads, channel); one 16-byte store per digit plane
+    // ---- (3) quantise from registers: one 16-byte store per group and digit plane
     {
-      const float s = scale[ch], inv = 1.f / s;
-      for (int grp = sub; grp < kQuads / 4; grp += kWarps) {
+      float m = red[ch];
+#pragma unroll
+      for (int k = 1; k < kWarps; ++k) m = fmaxf(m, red[k * kCh + ch]);
+      const float s = m > 0.f ? m / 127.f : 1.f, inv = 1.f / s;
+      if (sub == 0) scale[ch] = s;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
         unsigned w1[4], w2[4];
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          const float* px = sg + qtile[4 * grp + qq] + ch;
-          const float v[4] = {px[0], px[step1], px[step2], px[step3]};
-          w1[qq] = 0u;
-          w2[qq] = 0u;
+          unsigned b1[4], b2[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float x = v[k] * inv;
-            unsigned b1, b2;
-            const float q1 = round_magic(x, &b1);
-            const float r = fminf(fmaxf((x - q1) * 254.f, -127.f), 127.f);
-            round_magic(r, &b2);
-            w1[qq] |= (b1 & 0xffu) << (8 * k);
-            w2[qq] |= (b2 & 0xffu) << (8 * k);
-          }
+          for (int e = 0; e < 4; ++e) quantise(v[k][4 * qq + e] * inv, &b1[e], &b2[e]);
+          w1[qq] = pack4(b1[0], b1[1], b1[2], b1[3]);
+          w2[qq] = pack4(b2[0], b2[1], b2[2], b2[3]);
         }
-        uint8_t* at = gq + (grp * kCh + ch) * 16;
+        uint8_t* at = gq + ((sub + 8 * k) * kCh + ch) * 16;
         *reinterpret_cast<uint4*>(at) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         *reinterpret_cast<uint4*>(at + kGqPlane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
       }
+      if (extra) {
+        unsigned b1[4], b2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) quantise(vx[e] * inv, &b1[e], &b2[e]);
+        uint8_t* at = gq + (24 * kCh + ch) * 16 + 4 * sub;
+        *reinterpret_cast<unsigned*>(at) = pack4(b1[0], b1[1], b1[2], b1[3]);
+        *reinterpret_cast<unsigned*>(at + kGqPlane) = pack4(b2[0], b2[1], b2[2], b2[3]);
+      }
     }
-    fence_proxy_async_smem();   // the in-place masking wrote the tile the next bulk copy overwrites
-    __syncthreads();   // Zt and Gq complete; raw frame buffer `buf` and both tiles are consumed
-    if (tid == 0) {
-      if (f + 2 * stride < batch) load_frame(f + 2 * stride, buf);
-      if (f + stride < batch) load_tiles(f + stride);
-    }
+    __syncthreads();   // Zt, Gq and scale complete
 
     // ---- (4) MMAs: acc[m][n][plane] over 13 k32 steps (8 quads each)
     int acc[2][kNT][2][4];
@@ -252,40 +277,37 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 #pragma unroll 1
     for (int s = 0; s < kSteps; ++s) {
       const int quad0 = 8 * s + t, quad1 = quad0 + 4;       // this lane's two quads of the step
-      unsigned a[2][2][4];                                   // [m-tile][plane][a0..a3]
+      // byte offsets of the two quads inside a Zt plane, shifted by this warp's quadrant
+      const int off0 = qzt[quad0] + qa * kZtRow + qb, off1 = qzt[quad1] + qa * kZtRow + qb;
+      unsigned b[kNT][2];
+#pragma unroll
+      for (int n = 0; n < kNT; ++n) {
+        const int nt = ntile0 + n;
+        const uint8_t* plane = zt + ((nt >> 1) * 16 + 2 * g + (nt & 1)) * kZtTap;
+        if (qb == 0) {   // aligned
+          b[n][0] = *reinterpret_cast<const unsigned*>(plane + off0);
+          b[n][1] = *reinterpret_cast<const unsigned*>(plane + off1);
+        } else {         // bytes 1..4 of two aligned words
+          const unsigned* p0 = reinterpret_cast<const unsigned*>(plane + off0 - 1);
+          const unsigned* p1 = reinterpret_cast<const unsigned*>(plane + off1 - 1);
+          b[n][0] = __byte_perm(p0[0], p0[1], 0x4321);
+          b[n][1] = __byte_perm(p1[0], p1[1], 0x4321);
+        }
+      }
 #pragma unroll
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           // quads 8s + t and 8s + 4 + t live in groups 2s and 2s + 1 at word t
           const uint8_t* row = gq + p * kGqPlane + ((2 * s) * kCh + 16 * m + g) * 16 + 4 * t;
-          a[m][p][0] = *reinterpret_cast<const unsigned*>(row);
-          a[m][p][1] = *reinterpret_cast<const unsigned*>(row + 8 * 16);
-          a[m][p][2] = *reinterpret_cast<const unsigned*>(row + kCh * 16);
-          a[m][p][3] = *reinterpret_cast<const unsigned*>(row + (kCh + 8) * 16);
-        }
-      // byte offsets of the two quads inside a Zt tap plane, shifted by this warp's quadrant
-      const int off0 = qzt[quad0] + qa * kZtRow + qb, off1 = qzt[quad1] + qa * kZtRow + qb;
+          unsigned a[4];
+          a[0] = *reinterpret_cast<const unsigned*>(row);
+          a[1] = *reinterpret_cast<const unsigned*>(row + 8 * 16);
+          a[2] = *reinterpret_cast<const unsigned*>(row + kCh * 16);
+          a[3] = *reinterpret_cast<const unsigned*>(row + (kCh + 8) * 16);
 #pragma unroll
-      for (int n = 0; n < kNT; ++n) {
-        const int nt = ntile0 + n;
-        const uint8_t* plane = zt + ((nt >> 1) * 16 + 2 * g + (nt & 1)) * kZtTap;
-        unsigned b0, b1;
-        if (qb == 0) {   // aligned
-          b0 = *reinterpret_cast<const unsigned*>(plane + off0);
-          b1 = *reinterpret_cast<const unsigned*>(plane + off1);
-        } else {         // bytes 1..4 of two aligned words
-          const unsigned* p0 = reinterpret_cast<const unsigned*>(plane + off0 - 1);
-          const unsigned* p1 = reinterpret_cast<const unsigned*>(plane + off1 - 1);
-          b0 = __byte_perm(p0[0], p0[1], 0x4321);
-          b1 = __byte_perm(p1[0], p1[1], 0x4321);
+          for (int n = 0; n < kNT; ++n) mma_s8u8(acc[m][n][p], a, b[n][0], b[n][1]);
         }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_s8u8(acc[m][n][0], a[m][0], b0, b1);
-          mma_s8u8(acc[m][n][1], a[m][1], b0, b1);
-        }
-      }
     }
 
     // ---- (5) int32 -> fp32, apply the frame's per-channel scales
@@ -296,16 +318,16 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
       for (int n = 0; n < kNT; ++n) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float v = (float)acc[m][n][0][k] + (float)acc[m][n][1][k] * (1.f / 254.f);
-          wsum[m][n][k] += v * (k < 2 ? s_lo : s_hi);
+          const float x = (float)acc[m][n][0][k] + (float)acc[m][n][1][k] * (1.f / 254.f);
+          wsum[m][n][k] += x * (k < 2 ? s_lo : s_hi);
         }
       }
     }
-    __syncthreads();   // everyone is done with Zt / Gq / scale before the next frame rewrites them
+    __syncthreads();   // everyone is done with Zt / Gq / scale / red before the next frame
   }
 
   // ---- per-CTA partials: partial_w[cta][quadrant][tap][channel], partial_b[cta][channel]
-  float* pw = partial_w + (size_t)blockIdx.x * (4 * 64 * kCh) + (size_t)quadrant * (64 * kCh);
+  float* pw = partial_w + (size_t)blockIdx.x * kPartial + (size_t)quadrant * (64 * kCh);
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -330,17 +352,23 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 }
 
 // grad_w[n][c][4a+i][4b+j] = (1/255) * sum_cta partial_w[cta][a*2+b][(i*4+j)*4+c][n]
+// one thread per element of the partial layout (coalesced); four interleaved chains, fixed order
 __global__ void __launch_bounds__(256)
 stem_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restrict__ partial_b,
                        int ctas, float* __restrict__ grad_w, float* __restrict__ grad_b) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over [32][4][8][8]
-  if (e < kCh * 256) {
-    const int kw = e & 7, kh = (e >> 3) & 7, c = (e >> 6) & 3, n = e >> 8;
-    const int quadrant = (kh >> 2) * 2 + (kw >> 2), tap = ((kh & 3) * 4 + (kw & 3)) * 4 + c;
-    const float* p = partial_w + ((size_t)quadrant * 64 + tap) * kCh + n;
-    double s = 0.0;
-    for (int b = 0; b < ctas; ++b) s += (double)__ldg(p + (size_t)b * (4 * 64 * kCh));
-    grad_w[e] = (float)(s * (1.0 / 255.0));
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over [4 quadrants][64 taps][32 ch]
+  if (e < kPartial) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int b = 0;
+    for (; b + 4 <= ctas; b += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += (double)__ldg(partial_w + (size_t)(b + k) * kPartial + e);
+    }
+    for (; b < ctas; ++b) s[b & 3] += (double)__ldg(partial_w + (size_t)b * kPartial + e);
+    const int n = e & 31, tap = (e >> 5) & 63, quadrant = e >> 11;
+    const int c = tap & 3, j = (tap >> 2) & 3, i = tap >> 4;
+    const int kh = 4 * (quadrant >> 1) + i, kw = 4 * (quadrant & 1) + j;
+    grad_w[((n * 4 + c) * 8 + kh) * 8 + kw] = (float)(((s[0] + s[1]) + (s[2] + s[3])) * (1.0 / 255.0));
   }
   if (e < kCh) {
     double s = 0.0;
@@ -355,7 +383,7 @@ stem_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restr
 using namespace derl;
 
 extern "C" size_t derl_b200_stem_backward_workspace_bytes(void) {
-  return (size_t)sm_count() * (4 * 64 * kCh + kCh) * sizeof(float);
+  return (size_t)kCtasPerSm * sm_count() * (kPartial + kCh) * sizeof(float);
 }
 
 extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, const float* grad_out,
@@ -380,13 +408,14 @@ extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, con
                                    (int)BwdSmem::bytes));
     attr_set = true;
   }
-  long long grid = batch < sm_count() ? batch : sm_count();
+  const long long max_grid = (long long)kCtasPerSm * sm_count();
+  long long grid = batch < max_grid ? batch : max_grid;
   float* partial_w = reinterpret_cast<float*>(workspace);
-  float* partial_b = partial_w + (size_t)sm_count() * (4 * 64 * kCh);
+  float* partial_b = partial_w + (size_t)max_grid * kPartial;
   stem_bwd_kernel<<<(unsigned)grid, kThreads, BwdSmem::bytes, st>>>(
       frames, grad_out, out, partial_w, partial_b, batch, blocked);
   DERL_LAUNCH_CHECK("stem_bwd_kernel");
-  stem_bwd_reduce_kernel<<<(kCh * 256 + 255) / 256, 256, 0, st>>>(partial_w, partial_b, (int)grid,
+  stem_bwd_reduce_kernel<<<kPartial / 256, 256, 0, st>>>(partial_w, partial_b, (int)grid,
                                                                   grad_weight, grad_bias);
   DERL_LAUNCH_CHECK("stem_bwd_reduce_kernel");
   return DERL_OK;
