@@ -159,8 +159,59 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
     const float* gt = grad_out + f * (kPix * kCh) + ch;
     const float* ot = out + f * (kPix * kCh) + ch;
 
-    // ---- (0) issue this thread's gradient loads (each warp-load is one pixel: 128 contiguous B)
+    // ---- (0a) issue this thread's activation loads (each warp-load is one pixel: 128 contiguous B)
     float v[3][16], vx[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float* px = ot + qtile[4 * (sub + 8 * k) + qq];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[k][4 * qq + e] = __ldcs(px + step[e]);
+      }
+    {
+      const float* px = ot + qtile[96 + (sub & 3)];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) vx[e] = extra ? __ldcs(px + step[e]) : 0.f;
+    }
+
+    // ---- (1) byte transpose of the frame: Zt[c*16+i*4+j][Y][X] = raw[4Y+i][4X+j][c]
+    // one 4x4 byte block per lane and step: 4 source words (X..X+3, channels c=0..3 each) ->
+    // 4 destination words (planes c=0..3, bytes X..X+3).
+    // lane = j + 4*(xg & 1) + 8*i makes the 32 source words of a warp hit 32 distinct banks.
+    // Done in two halves, each covering the latency of one set of global loads.
+    auto transpose_blocks = [&](int blk_begin, int blk_end) {
+      for (int blk = blk_begin + warp; blk < blk_end; blk += kWarps) {
+        const int Y = blk / 3, xg = (blk - Y * 3) * 2 + ((lane >> 2) & 1);
+        const int i = lane >> 3, j = lane & 3, ij = i * 4 + j;
+        const uint8_t* src = raw + (4 * Y + i) * 336 + (16 * xg + j) * 4;
+        unsigned w0 = *reinterpret_cast<const unsigned*>(src);
+        unsigned w1 = *reinterpret_cast<const unsigned*>(src + 16);
+        unsigned w2 = *reinterpret_cast<const unsigned*>(src + 32);
+        unsigned w3 = *reinterpret_cast<const unsigned*>(src + 48);
+        // 4x4 byte transpose (rows w0..w3, columns = channel bytes)
+        const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
+        const unsigned t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
+        const unsigned c0 = __byte_perm(t0, t2, 0x5410), c1 = __byte_perm(t0, t2, 0x7632);
+        const unsigned c2 = __byte_perm(t1, t3, 0x5410), c3 = __byte_perm(t1, t3, 0x7632);
+        uint8_t* dst = zt + ij * kZtTap + Y * kZtRow + 4 * xg;
+        *reinterpret_cast<unsigned*>(dst) = c0;
+        *reinterpret_cast<unsigned*>(dst + 16 * kZtTap) = c1;
+        *reinterpret_cast<unsigned*>(dst + 32 * kZtTap) = c2;
+        *reinterpret_cast<unsigned*>(dst + 48 * kZtTap) = c3;
+      }
+    };
+    mbar_wait(bar, (unsigned)(it & 1));
+    transpose_blocks(0, 32);
+
+    // ---- (0b) activations -> ReLU mask bits; issue the gradient loads into the same registers
+    unsigned keep[3] = {0u, 0u, 0u}, keepx = 0u;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) keep[k] |= (v[k][e] > 0.f ? 1u : 0u) << e;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) keepx |= (vx[e] > 0.f ? 1u : 0u) << e;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -174,56 +225,25 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 #pragma unroll
       for (int e = 0; e < 4; ++e) vx[e] = extra ? __ldcs(px + step[e]) : 0.f;
     }
+    transpose_blocks(32, 21 * 3);
 
-    // ---- (1) byte transpose of the frame: Zt[c*16+i*4+j][Y][X] = raw[4Y+i][4X+j][c]
-    // one 4x4 byte block per lane and step: 4 source words (X..X+3, channels c=0..3 each) ->
-    // 4 destination words (planes c=0..3, bytes X..X+3).
-    // lane = j + 4*(xg & 1) + 8*i makes the 32 source words of a warp hit 32 distinct banks
-    mbar_wait(bar, (unsigned)(it & 1));
-    for (int blk = warp; blk < 21 * 3; blk += kWarps) {
-      const int Y = blk / 3, xg = (blk - Y * 3) * 2 + ((lane >> 2) & 1);
-      const int i = lane >> 3, j = lane & 3, ij = i * 4 + j;
-      const uint8_t* src = raw + (4 * Y + i) * 336 + (16 * xg + j) * 4;
-      unsigned w0 = *reinterpret_cast<const unsigned*>(src);
-      unsigned w1 = *reinterpret_cast<const unsigned*>(src + 16);
-      unsigned w2 = *reinterpret_cast<const unsigned*>(src + 32);
-      unsigned w3 = *reinterpret_cast<const unsigned*>(src + 48);
-      // 4x4 byte transpose (rows w0..w3, columns = channel bytes)
-      const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
-      const unsigned t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
-      const unsigned c0 = __byte_perm(t0, t2, 0x5410), c1 = __byte_perm(t0, t2, 0x7632);
-      const unsigned c2 = __byte_perm(t1, t3, 0x5410), c3 = __byte_perm(t1, t3, 0x7632);
-      uint8_t* dst = zt + ij * kZtTap + Y * kZtRow + 4 * xg;
-      *reinterpret_cast<unsigned*>(dst) = c0;
-      *reinterpret_cast<unsigned*>(dst + 16 * kZtTap) = c1;
-      *reinterpret_cast<unsigned*>(dst + 32 * kZtTap) = c2;
-      *reinterpret_cast<unsigned*>(dst + 48 * kZtTap) = c3;
-    }
-
-    // ---- (2) ReLU mask, per-channel max and bias sum, values stay in registers
+    // ---- (2) apply the mask; per-channel max and bias sum; values stay in registers
     float vmax = 0.f, vsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const float* px = ot + qtile[4 * (sub + 8 * k) + qq];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float gv = __ldcs(px + step[e]) > 0.f ? v[k][4 * qq + e] : 0.f;
-          v[k][4 * qq + e] = gv;
-          vmax = fmaxf(vmax, fabsf(gv));
-          vsum += gv;
-        }
-      }
-    if (extra) {
-      const float* px = ot + qtile[96 + sub];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gv = __ldcs(px + step[e]) > 0.f ? vx[e] : 0.f;
-        vx[e] = gv;
+      for (int e = 0; e < 16; ++e) {
+        const float gv = (keep[k] >> e) & 1u ? v[k][e] : 0.f;
+        v[k][e] = gv;
         vmax = fmaxf(vmax, fabsf(gv));
         vsum += gv;
       }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gv = (keepx >> e) & 1u ? vx[e] : 0.f;
+      vx[e] = gv;
+      vmax = fmaxf(vmax, fabsf(gv));
+      vsum += gv;
     }
     bsum += vsum;
     red[sub * kCh + ch] = vmax;
