@@ -4,8 +4,8 @@ The reference re-uploads every minibatch from NumPy (`torch.from_numpy(...).to(d
 derl/models.py:79-88).  The resident-rollout design uploads once — but a blocking copy of a
 14.8 GB frame-stack column puts ~0.3 s of PCIe time in front of the update.  `HostColumn`
 removes that serial phase: during the first epoch each minibatch's rows are pulled straight
-from the pinned host array by the TMA gather kernel running on a side stream (concurrently
-with the previous minibatch's update) and written BOTH to the minibatch and to their home
+from the pinned host array by the TMA gather kernel running on a side stream (one minibatch
+ahead of the consumer, i.e. concurrently with the previous minibatch's update) and written BOTH to the minibatch and to their home
 position in the device-resident copy (`derl_b200_gather_rows_upload`).  One epoch's
 minibatches partition the rollout, so after the first epoch the column is fully resident and
 later epochs gather from HBM.  Any other access pattern falls back to one bulk upload.
@@ -33,8 +33,9 @@ def eligible(array):
 
 
 class HostColumn:
-  def __init__(self, host, device, max_ctas=8):
+  def __init__(self, host, device, max_ctas=8, prefetch=True):
     self.host, self.device, self.max_ctas = host, torch.device(device), max_ctas
+    self.prefetch, self._ahead = prefetch, None
     self.resident = None
     self.complete = False
     self._perm, self._covered = None, 0
@@ -70,29 +71,48 @@ class HostColumn:
       self.complete = True
     return self.resident
 
-  def gather(self, perm, start, count, perm_ready=None):
-    """Rows perm[start:start+count] as a device tensor."""
-    if self.complete:
-      return _K.gather_rows(self.resident, perm, start, count)
-    sequential = (self._perm is None and start == 0) or (self._perm is perm and
-                                                         start == self._covered)
-    if not sequential or not self._row_ok() or perm.numel() != self.host.shape[0]:
-      return _K.gather_rows(self.materialize(), perm, start, count)
-    self._perm = perm
+  def _issue(self, perm, start, count):
+    """Enqueue one upload + gather on the side stream -> (rows, completion event)."""
     resident = self._ensure_resident()
-    main = torch.cuda.current_stream(self.device)
-    if self._stream is None:
-      self._stream = torch.cuda.Stream(self.device, priority=-1)
-      self._stream.wait_stream(main)        # resident allocation / anything before the rollout
-    elif perm_ready is not None:
-      self._stream.wait_event(perm_ready)
     with torch.cuda.stream(self._stream):
       rows = _K.gather_rows_upload(self.host.data_ptr(), perm, start, count, resident,
                                    self.max_ctas)
       done = self._stream.record_event()
+    return rows, done
+
+  def gather(self, perm, start, count, perm_ready=None):
+    """Rows perm[start:start+count] as a device tensor.  During the first epoch the NEXT range
+    of the same size is enqueued on the side stream right away, so that PCIe stays busy while
+    the caller is still enqueueing (or running) the update on the current range."""
+    if self.complete:
+      return _K.gather_rows(self.resident, perm, start, count)
+    nrows = self.host.shape[0]
+    sequential = (self._perm is None and start == 0) or (self._perm is perm and
+                                                         start == self._covered)
+    ahead, self._ahead = self._ahead, None
+    if ahead is not None and ahead[0] != (start, count):
+      sequential = False                     # the prefetched range is not the one asked for
+    if not sequential or not self._row_ok() or perm.numel() != nrows:
+      return _K.gather_rows(self.materialize(), perm, start, count)
+    self._perm = perm
+    main = torch.cuda.current_stream(self.device)
+    if self._stream is None:
+      self._ensure_resident()
+      self._stream = torch.cuda.Stream(self.device, priority=-1)
+      self._stream.wait_stream(main)        # resident allocation / anything before the rollout
+    if ahead is not None:
+      rows, done = ahead[1], ahead[2]
+    else:
+      if perm_ready is not None:
+        self._stream.wait_event(perm_ready)
+      rows, done = self._issue(perm, start, count)
+    following = start + count
+    if self.prefetch and following < nrows:
+      ahead_count = min(count, nrows - following)
+      self._ahead = ((following, ahead_count),) + self._issue(perm, following, ahead_count)
     main.wait_event(done)
     rows.record_stream(main)
-    self._covered = start + count
-    if self._covered == self.host.shape[0]:
+    self._covered = following
+    if self._covered == nrows:
       self.complete = True                   # every row now has its home copy in HBM
     return rows
