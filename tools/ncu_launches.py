@@ -26,7 +26,8 @@ step = rows[start:]
 tot = sum(t for _, t in step)
 agg = defaultdict(lambda: [0, 0.0])
 for n, t in step:
-  short = re.sub(r"<.*", "", n)
+  short = n.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
+  short = re.sub(r"<.*", "", short)
   short = re.sub(r"\(.*", "", short)[:70]
   agg[short][0] += 1
   agg[short][1] += t
