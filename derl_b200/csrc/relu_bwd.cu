@@ -8,7 +8,7 @@
 //     grad_pre[r, c] = out[r, c] > 0 ? grad_out[r, c] : 0          (written once)
 //     bias_grad[c]   = sum_r grad_pre[r, c]                        (float32 accumulate)
 // 3 x sizeof(T) bytes per element instead of 4 x, and one launch instead of two.  The
-// cross-block sum uses per-block partials reduced by the last block in fixed order
+// cross-block sum uses per-block partials reduced by the last block in a fixed order
 // (deterministic, no float atomics).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -130,12 +130,25 @@ relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < quads) {  // last block: sum the per-block partials in block order
+  // last block: every thread sums a strided subset of the per-block partials (slot k takes blocks
+  // k, k + rpb, ...: many independent loads in flight), then a fixed-order sum over the slots
+  __shared__ double wide[kThreads][4];
+  {
     double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (unsigned b = 0; b < gridDim.x; ++b) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(partials) + (size_t)b * quads +
-                              threadIdx.x);
+#pragma unroll 8
+    for (unsigned b = threadIdx.x / quads; b < gridDim.x; b += rpb) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partials) + (size_t)b * quads + quad);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wide[threadIdx.x][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < quads) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < rpb; ++k) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] += wide[threadIdx.x + k * quads][c];
     }
     reinterpret_cast<float4*>(bias_grad)[threadIdx.x] =
         make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);

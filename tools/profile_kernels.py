@@ -101,6 +101,12 @@ def main():
   gact = torch.randn_like(act)
   timed("relu_bwd_bias 32768x32x20x20", lambda: K.relu_bwd_bias(gact, act), 12.0 * act.numel())
   del act, gact
+  for hw in (9, 7):   # the conv2 / conv3 activations of a 32768-frame micro-batch
+    act = torch.relu(torch.randn(32768, 64, hw, hw, device=DEV, generator=gen)).contiguous(
+        memory_format=torch.channels_last)
+    gact = torch.randn_like(act)
+    timed(f"relu_bwd_bias 32768x64x{hw}x{hw}", lambda: K.relu_bwd_bias(gact, act), 12.0 * act.numel())
+    del act, gact
   cols = [adv.repeat(4), vt.reshape(-1).repeat(4), vold.reshape(-1).repeat(4), old_lp.repeat(4),
           acts.repeat(4)]
   timed("gather_columns 5 cols", lambda: K.gather_columns(cols, perm, mb, mb, 0),
