@@ -372,28 +372,36 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
 }
 
 // grad_w[n][c][4a+i][4b+j] = (1/255) * sum_cta partial_w[cta][a*2+b][(i*4+j)*4+c][n]
-// one thread per element of the partial layout (coalesced); four interleaved chains, fixed order
+// Blocks 0 .. kPartial/32 - 1 take 32 consecutive elements of the partial layout (one 128-byte
+// line per CTA partial); the block's 8 warps sum interleaved subsets of the CTAs and the subsets
+// are then added in fixed order.  The last block sums the bias partials the same way.
 __global__ void __launch_bounds__(256)
 stem_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restrict__ partial_b,
                        int ctas, float* __restrict__ grad_w, float* __restrict__ grad_b) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over [4 quadrants][64 taps][32 ch]
-  if (e < kPartial) {
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    int b = 0;
-    for (; b + 4 <= ctas; b += 4) {
+  constexpr int kSlots = 8;
+  __shared__ double slot[kSlots][32];
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+  const bool bias = blockIdx.x == kPartial / 32;
+  const float* src = bias ? partial_b + lane : partial_w + (size_t)blockIdx.x * 32 + lane;
+  const size_t pitch = bias ? kCh : kPartial;
+  double s = 0.0;
+#pragma unroll 4
+  for (int b = k; b < ctas; b += kSlots) s += (double)__ldg(src + (size_t)b * pitch);
+  slot[k][lane] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double total = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] += (double)__ldg(partial_w + (size_t)(b + k) * kPartial + e);
+    for (int q = 0; q < kSlots; ++q) total += slot[q][lane];
+    if (bias) {
+      grad_b[lane] = (float)total;
+    } else {
+      const int e = blockIdx.x * 32 + lane;   // over [4 quadrants][64 taps][32 ch]
+      const int n = e & 31, tap = (e >> 5) & 63, quadrant = e >> 11;
+      const int c = tap & 3, j = (tap >> 2) & 3, i = tap >> 4;
+      const int kh = 4 * (quadrant >> 1) + i, kw = 4 * (quadrant & 1) + j;
+      grad_w[((n * 4 + c) * 8 + kh) * 8 + kw] = (float)(total * (1.0 / 255.0));
     }
-    for (; b < ctas; ++b) s[b & 3] += (double)__ldg(partial_w + (size_t)b * kPartial + e);
-    const int n = e & 31, tap = (e >> 5) & 63, quadrant = e >> 11;
-    const int c = tap & 3, j = (tap >> 2) & 3, i = tap >> 4;
-    const int kh = 4 * (quadrant >> 1) + i, kw = 4 * (quadrant & 1) + j;
-    grad_w[((n * 4 + c) * 8 + kh) * 8 + kw] = (float)(((s[0] + s[1]) + (s[2] + s[3])) * (1.0 / 255.0));
-  }
-  if (e < kCh) {
-    double s = 0.0;
-    for (int b = 0; b < ctas; ++b) s += (double)__ldg(partial_b + (size_t)b * kCh + e);
-    grad_b[e] = (float)s;
   }
 }
 
@@ -435,7 +443,7 @@ extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, con
   stem_bwd_kernel<<<(unsigned)grid, kThreads, BwdSmem::bytes, st>>>(
       frames, grad_out, out, partial_w, partial_b, batch, blocked);
   DERL_LAUNCH_CHECK("stem_bwd_kernel");
-  stem_bwd_reduce_kernel<<<kPartial / 256, 256, 0, st>>>(partial_w, partial_b, (int)grid,
+  stem_bwd_reduce_kernel<<<kPartial / 32 + 1, 256, 0, st>>>(partial_w, partial_b, (int)grid,
                                                                   grad_weight, grad_bias);
   DERL_LAUNCH_CHECK("stem_bwd_reduce_kernel");
   return DERL_OK;
