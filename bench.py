@@ -452,8 +452,9 @@ def run_ours(args, rank, world, local):
     sec_h, _ = timed_updates(alg_h, runner_h, nbatches, args.steps, 1, world, True)
     perm_bytes = args.epochs * horizon * nenvs * 8
     e2e = {"value": samples_per_step * args.steps / sec_h, "unit": "samples/s",
-           "h2d_bytes_per_step": host_source.bytes + perm_bytes,
-           "d2h_bytes_per_step": nenvs * 4 + nbatches * 4, "ms_per_step": sec_h / args.steps * 1e3}
+           "h2d_bytes_per_step": world * (host_source.bytes + perm_bytes),
+           "d2h_bytes_per_step": world * (nenvs * 4 + nbatches * 4),
+           "ms_per_step": sec_h / args.steps * 1e3}
     del host_source, alg_h, runner_h
 
   sweep = gae_sweep(d, hbm_peak) if (args.gae_sweep and rank == 0) else None
@@ -495,7 +496,19 @@ def main():
     return
   if world > 1:
     from derl_b200 import parallel
-    parallel.init_from_env("nccl")
+    # NCCL announces its version on stdout when the first communicator comes up; stdout is
+    # reserved for the one JSON line, so point fd 1 at stderr until that has happened
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      parallel.init_from_env("nccl")
+      torch.distributed.all_reduce(torch.zeros(1, device=f"cuda:{local}"))
+      torch.cuda.synchronize()
+    finally:
+      sys.stdout.flush()
+      os.dup2(saved, 1)
+      os.close(saved)
   run_ours(args, rank, world, local)
   if world > 1:
     torch.distributed.destroy_process_group()
