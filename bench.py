@@ -150,6 +150,8 @@ def cpu_update_throughput(args, nenvs, steps, warmup):
   NatureCNN/PPOLoss/Adam) on a bounded sample of the workload; returns samples/s."""
   from oracle import derl_oracle as O
   import derl_b200 as d
+  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
+  torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
   torch.manual_seed(0)
   model = O.NatureCNN(args.nactions)
   optimizer = torch.optim.Adam(model.parameters(), lr=HP["lr"], eps=HP["eps"])
