@@ -74,9 +74,9 @@ __device__ __forceinline__ void mma_u8s8(int (&d)[4], const unsigned (&a)[4], un
 
 template <typename OT>
 __global__ void __launch_bounds__(kI8Threads)
-stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ weight,
-                         const float* __restrict__ bias, OT* __restrict__ out, long long batch,
-                         int out_block) {
+stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __restrict__ rows,
+                         const float* __restrict__ weight, const float* __restrict__ bias,
+                         OT* __restrict__ out, long long batch, int out_block) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint4* wsm = reinterpret_cast<uint4*>(smem + StemI8Smem::w_off);
   float* ssm = reinterpret_cast<float*>(smem + StemI8Smem::scale_off);
@@ -93,8 +93,9 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const float* __rest
     for (int b = 0; b < 2; ++b) {
       if (first + b * stride < batch) {
         mbar_expect_tx(&full[b], kImgBytes);
+        const long long i = first + b * stride;   // rows: fused minibatch gather (frame i = row rows[i])
         bulk_g2s(smem + StemI8Smem::raw_off + (size_t)b * kImgBytes,
-                 frames + (first + b * stride) * kImgBytes, kImgBytes, &full[b]);
+                 frames + (rows ? __ldg(rows + i) : i) * kImgBytes, kImgBytes, &full[b]);
       }
     }
   }
@@ -181,8 +182,9 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const float* __rest
     __syncthreads();  // all warps are done with raw[buf]: refill it with the frame after next
     if (tid == 0 && f + 2 * stride < batch) {
       mbar_expect_tx(&full[buf], kImgBytes);
+      const long long i = f + 2 * stride;
       bulk_g2s(smem + StemI8Smem::raw_off + (size_t)buf * kImgBytes,
-               frames + (f + 2 * stride) * kImgBytes, kImgBytes, &full[buf]);
+               frames + (rows ? __ldg(rows + i) : i) * kImgBytes, kImgBytes, &full[buf]);
     }
 
     OT* dst = out + f * (long long)(kPix * kOutC);
@@ -218,8 +220,8 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const float* __rest
 }
 
 template <typename OT>
-int launch(const uint8_t* frames, const float* weight, const float* bias, void* out,
-           long long batch, int out_block, cudaStream_t st) {
+int launch(const uint8_t* frames, const long long* rows, const float* weight, const float* bias,
+           void* out, long long batch, int out_block, cudaStream_t st) {
   auto kern = stem_conv_relu_i8_kernel<OT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -231,7 +233,7 @@ int launch(const uint8_t* frames, const float* weight, const float* bias, void* 
   const long long cap = (long long)sm_count() * 2;
   if (grid > cap) grid = cap;
   kern<<<(unsigned)grid, kI8Threads, StemI8Smem::bytes, st>>>(
-      frames, weight, bias, reinterpret_cast<OT*>(out), batch, out_block);
+      frames, rows, weight, bias, reinterpret_cast<OT*>(out), batch, out_block);
   DERL_LAUNCH_CHECK("stem_conv_relu_i8_kernel");
   return DERL_OK;
 }
@@ -241,9 +243,9 @@ int launch(const uint8_t* frames, const float* weight, const float* bias, void* 
 
 using namespace derl;
 
-extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, int64_t batch, const float* weight,
-                                        const float* bias, void* out, int out_dtype,
-                                        int out_block, void* stream) {
+extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, const int64_t* rows, int64_t batch,
+                                        const float* weight, const float* bias, void* out,
+                                        int out_dtype, int out_block, void* stream) {
   DERL_REQUIRE(out_block == 1 || out_block == 2, "stem_conv_relu: out_block must be 1 or 2");
   DERL_REQUIRE(frames && weight && bias && out && batch >= 0, "stem_conv_relu: bad arguments");
   DERL_REQUIRE(out_dtype == DERL_DTYPE_F32 || out_dtype == DERL_DTYPE_BF16,
@@ -255,6 +257,8 @@ extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, int64_t batch, co
   if (batch == 0) return DERL_OK;
   cudaStream_t st = as_stream(stream);
   return out_dtype == DERL_DTYPE_BF16
-             ? launch<__nv_bfloat16>(frames, weight, bias, out, batch, out_block, st)
-             : launch<float>(frames, weight, bias, out, batch, out_block, st);
+             ? launch<__nv_bfloat16>(frames, reinterpret_cast<const long long*>(rows), weight, bias,
+                                     out, batch, out_block, st)
+             : launch<float>(frames, reinterpret_cast<const long long*>(rows), weight, bias, out,
+                             batch, out_block, st);
 }

@@ -91,9 +91,10 @@ __device__ __forceinline__ unsigned pack4(unsigned a, unsigned b, unsigned c, un
 // grad_out / out: [B, 400, 32] float32 tiles (plain pixel order, or space-to-depth(2) order when
 // blocked != 0); partial_w: [grid][4 quadrants][64 taps][32 ch]; partial_b: [grid][32].
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ grad_out,
-                const float* __restrict__ out, float* __restrict__ partial_w,
-                float* __restrict__ partial_b, long long batch, int blocked) {
+stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict__ rows,
+                const float* __restrict__ grad_out, const float* __restrict__ out,
+                float* __restrict__ partial_w, float* __restrict__ partial_b, long long batch,
+                int blocked) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* raw = smem + BwdSmem::frame_off;
   uint8_t* zt = smem + BwdSmem::zt_off;
@@ -108,9 +109,9 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ gr
   const int g = lane >> 2, t = lane & 3;
   const long long first = blockIdx.x, stride = gridDim.x;
 
-  auto load_frame = [&](long long f) {
+  auto load_frame = [&](long long f) {   // rows: fused minibatch gather (frame f = row rows[f])
     mbar_expect_tx(bar, kFrameBytes);
-    bulk_g2s(raw, frames + f * kFrameBytes, kFrameBytes, bar);
+    bulk_g2s(raw, frames + (rows ? __ldg(rows + f) : f) * kFrameBytes, kFrameBytes, bar);
   };
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -414,8 +415,9 @@ extern "C" size_t derl_b200_stem_backward_workspace_bytes(void) {
   return (size_t)kCtasPerSm * sm_count() * (kPartial + kCh) * sizeof(float);
 }
 
-extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, const float* grad_out,
-                                       const float* out, int blocked, float* grad_weight,
+extern "C" int derl_b200_stem_backward(const uint8_t* frames, const int64_t* rows, int64_t batch,
+                                       const float* grad_out, const float* out, int blocked,
+                                       float* grad_weight,
                                        float* grad_bias, void* workspace, size_t workspace_bytes,
                                        void* stream) {
   DERL_REQUIRE(frames && grad_out && out && grad_weight && grad_bias && workspace && batch >= 1,
@@ -441,7 +443,8 @@ extern "C" int derl_b200_stem_backward(const uint8_t* frames, int64_t batch, con
   float* partial_w = reinterpret_cast<float*>(workspace);
   float* partial_b = partial_w + (size_t)max_grid * kPartial;
   stem_bwd_kernel<<<(unsigned)grid, kThreads, BwdSmem::bytes, st>>>(
-      frames, grad_out, out, partial_w, partial_b, batch, blocked);
+      frames, reinterpret_cast<const long long*>(rows), grad_out, out, partial_w, partial_b, batch,
+      blocked);
   DERL_LAUNCH_CHECK("stem_bwd_kernel");
   stem_bwd_reduce_kernel<<<kPartial / 32 + 1, 256, 0, st>>>(partial_w, partial_b, (int)grid,
                                                                   grad_weight, grad_bias);

@@ -103,10 +103,12 @@ class _StemConvReLU(torch.autograd.Function):
   the float frames only here, cuDNN wgrad), mapped back to [32, 4, 8, 8]."""
 
   @staticmethod
-  def forward(ctx, frames, weight, bias, dtype, out_block):
-    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype, out_block)
+  def forward(ctx, frames, weight, bias, dtype, out_block, rows=None):
+    """rows: int64 indices — the batch is frames[rows], read in place (fused minibatch gather)."""
+    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype, out_block,
+                                             rows)
     out = out.permute(0, 3, 1, 2)   # channels-last storage seen as NCHW
-    ctx.save_for_backward(frames, out)
+    ctx.save_for_backward(frames, out, rows)
     ctx.weight_dtype, ctx.out_block = weight.dtype, out_block
     return out
 
@@ -114,12 +116,14 @@ class _StemConvReLU(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, grad_out):
-    frames, out = ctx.saved_tensors
+    frames, out, rows = ctx.saved_tensors
     grad_out = grad_out.contiguous(memory_format=torch.channels_last)
     if _StemConvReLU.fused_backward and out.dtype == torch.float32:
       grad_w, grad_b = torch.ops.derl_b200.stem_backward(frames, grad_out, out,
-                                                         ctx.out_block == 2)
-      return None, grad_w.to(ctx.weight_dtype), grad_b, None, None
+                                                         ctx.out_block == 2, rows)
+      return None, grad_w.to(ctx.weight_dtype), grad_b, None, None, None
+    if rows is not None:   # the library route below wants the batch's frames as one tensor
+      frames = torch.ops.derl_b200.gather_rows(frames, rows, 0, rows.numel())
     # out_block 2: [B,128,10,10] with (i, j, c) channels; K5 stores the masked gradient
     # straight in the plain [B,32,20,20] layout the weight-gradient conv needs
     grad_pre, grad_b = torch.ops.derl_b200.relu_bwd_bias(grad_out, out, ctx.out_block)
@@ -132,7 +136,7 @@ class _StemConvReLU(torch.autograd.Function):
         [False, True, False])
     # [O, (i, j, c), a, b] -> [O, c, 4a + i, 4b + j]
     grad_w = grad_w2.reshape(32, 4, 4, 4, 2, 2).permute(0, 3, 4, 1, 5, 2).reshape(32, 4, 8, 8)
-    return None, grad_w.to(ctx.weight_dtype), grad_b, None, None
+    return None, grad_w.to(ctx.weight_dtype), grad_b, None, None, None
 
 
 def _conv_out(size, conv):
@@ -218,6 +222,8 @@ class NatureCNNBase(nn.Sequential):
     conv = self[0]
     s = conv.stride[0]
     from . import ops  # noqa: F401  (registers torch.ops.derl_b200)
+    from .runners.row_selection import RowSelection
+    selection = frames if isinstance(frames, RowSelection) else None
     autocast = torch.is_autocast_enabled("cuda")
     dtype = torch.get_autocast_dtype("cuda") if autocast else conv.weight.dtype
     pre_s2d = False
@@ -227,8 +233,14 @@ class NatureCNNBase(nn.Sequential):
       nxt = list(self.children())[2]
       pre_s2d = (self.space_to_depth and self.space_to_depth_hidden and isinstance(nxt, nn.Conv2d)
                  and nxt.stride == (2, 2) and self._s2d_ok(nxt, 20, 20))
-      hidden = _StemConvReLU.apply(frames, conv.weight, conv.bias, dtype, 2 if pre_s2d else 1)
+      if selection is not None:   # fused gather: the stem kernels read the rollout rows in place
+        hidden = _StemConvReLU.apply(selection.source, conv.weight, conv.bias, dtype,
+                                     2 if pre_s2d else 1, selection.rows)
+      else:
+        hidden = _StemConvReLU.apply(frames, conv.weight, conv.bias, dtype, 2 if pre_s2d else 1)
     else:
+      if selection is not None:
+        frames = selection.materialize()
       s2d = torch.ops.derl_b200.frames_to_s2d(frames, s, dtype, 255.0).permute(0, 3, 1, 2)
       weight, bias = self._s2d_weight(conv), conv.bias
       if self.fused_conv_relu:
@@ -269,6 +281,8 @@ class NatureCNNBase(nn.Sequential):
     inputs, = _collocate(self, [inputs], cast_dtype=False)
     if self._s2d_applies(inputs):
       return self._forward_frames(inputs)
+    if hasattr(inputs, "materialize"):   # a RowSelection on a path without the fused stem
+      inputs = inputs.materialize()
     if self.permute:
       inputs = inputs.permute(0, 3, 1, 2)   # NHWC storage seen as NCHW == channels_last
     if inputs.dtype == torch.uint8:

@@ -340,11 +340,13 @@ space_to_depth.register_autograd(_s2d_backward, setup_context=_s2d_setup)
 # --------------------------------------------------------------------------- K6: stem conv
 @torch.library.custom_op("derl_b200::stem_conv_relu", mutates_args=(), device_types="cuda")
 def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dtype,
-                   out_block: int = 1) -> Tensor:
+                   out_block: int = 1, rows: Optional[Tensor] = None) -> Tensor:
   """relu(conv2d(frames/255, weight, bias, stride 4)) for uint8 NHWC frames [B,84,84,4] and the
   Atari stem weight [32,4,8,8]; returns the channels-last activation [B,20,20,32], or its
-  space-to-depth(2) arrangement [B,10,10,128] when out_block == 2."""
+  space-to-depth(2) arrangement [B,10,10,128] when out_block == 2.  `rows` (int64 [B']): the
+  batch is frames[rows] — the minibatch gather fused into the layer, nothing materialised."""
   _dense(frames, "frames", (torch.uint8,))
+  batch = _check_rows(frames, rows)
   _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
   _dense(weight, "weight", (torch.float32,))
   _dense(bias, "bias", (torch.float32,))
@@ -352,30 +354,46 @@ def stem_conv_relu(frames: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dt
         "stem_conv_relu is specialised to weight [32,4,8,8], bias [32]")
   _need(dtype in (torch.float32, torch.bfloat16), "dtype must be float32 or bfloat16")
   _need(out_block in (1, 2), "out_block must be 1 or 2")
-  shape = (frames.shape[0], 20, 20, 32) if out_block == 1 else (frames.shape[0], 10, 10, 128)
+  shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
   out = torch.empty(shape, dtype=dtype, device=frames.device)
   with _device_of(frames, "stem_conv_relu"):
-    _lib.check(_lib.load().derl_b200_stem_conv_relu(_p(frames), frames.shape[0], _p(weight),
-                                                    _p(bias), _p(out), _S2D_DTYPES[dtype],
-                                                    out_block, _stream(frames)), "stem_conv_relu")
+    _lib.check(_lib.load().derl_b200_stem_conv_relu(
+        _p(frames), _p(rows) if rows is not None else None, batch, _p(weight), _p(bias), _p(out),
+        _S2D_DTYPES[dtype], out_block, _stream(frames)), "stem_conv_relu")
   return out
 
 
+def _check_rows(frames, rows):
+  """Batch size of a (frames, rows) pair; rows must be a dense int64 vector on frames' device."""
+  if rows is None:
+    return frames.shape[0]
+  _dense(rows, "rows", (torch.int64,))
+  _need(rows.dim() == 1 and rows.device == frames.device, "rows must be a 1-D tensor on the "
+        "frames' device")
+  if CHECK_INDICES and rows.numel():
+    lo, hi = int(rows.min()), int(rows.max())
+    _need(0 <= lo and hi < frames.shape[0], f"rows out of range [0, {frames.shape[0]})")
+  return rows.numel()
+
+
 @stem_conv_relu.register_fake
-def _(frames, weight, bias, dtype, out_block=1):
-  shape = (frames.shape[0], 20, 20, 32) if out_block == 1 else (frames.shape[0], 10, 10, 128)
+def _(frames, weight, bias, dtype, out_block=1, rows=None):
+  batch = frames.shape[0] if rows is None else rows.shape[0]
+  shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
   return frames.new_empty(shape, dtype=dtype)
 
 
 @torch.library.custom_op("derl_b200::stem_backward", mutates_args=(), device_types="cuda")
-def stem_backward(frames: Tensor, grad_out: Tensor, out: Tensor,
-                  blocked: bool) -> Tuple[Tensor, Tensor]:
+def stem_backward(frames: Tensor, grad_out: Tensor, out: Tensor, blocked: bool,
+                  rows: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
   """(grad_weight [32,4,8,8], grad_bias [32]) of relu(conv2d(frames/255, W, b, stride 4)) given
   the gradient w.r.t. its output and the saved output: channels-last [B,32,20,20] tensors, or
   their space-to-depth(2) arrangement [B,128,10,10] when `blocked`."""
   _dense(frames, "frames", (torch.uint8,))
   _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
-  want = (frames.shape[0], 128, 10, 10) if blocked else (frames.shape[0], 32, 20, 20)
+  batch = _check_rows(frames, rows)
+  _need(batch >= 1, "stem_backward needs at least one frame")
+  want = (batch, 128, 10, 10) if blocked else (batch, 32, 20, 20)
   for name, t in (("grad_out", grad_out), ("out", out)):
     _need(t.dtype == torch.float32 and tuple(t.shape) == want
           and t.is_contiguous(memory_format=torch.channels_last),
@@ -386,14 +404,14 @@ def stem_backward(frames: Tensor, grad_out: Tensor, out: Tensor,
   ws_bytes = lib.derl_b200_stem_backward_workspace_bytes()
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
   with _device_of(frames, "stem_backward"):
-    _lib.check(lib.derl_b200_stem_backward(_p(frames), frames.shape[0], _p(grad_out), _p(out),
-                                           int(blocked), _p(grad_w), _p(grad_b), _p(ws), ws_bytes,
-                                           _stream(frames)), "stem_backward")
+    _lib.check(lib.derl_b200_stem_backward(
+        _p(frames), _p(rows) if rows is not None else None, batch, _p(grad_out), _p(out),
+        int(blocked), _p(grad_w), _p(grad_b), _p(ws), ws_bytes, _stream(frames)), "stem_backward")
   return grad_w, grad_b
 
 
 @stem_backward.register_fake
-def _(frames, grad_out, out, blocked):
+def _(frames, grad_out, out, blocked, rows=None):
   return frames.new_empty((32, 4, 8, 8), dtype=torch.float32), \
       frames.new_empty(32, dtype=torch.float32)
 

@@ -18,6 +18,7 @@ import torch
 from .. import _lib, ops  # noqa: F401
 from .env_runner import EnvRunner, RunnerWrapper
 from .host_column import HostColumn, eligible as _lazy_eligible
+from .row_selection import RowSelection
 from .summary import PeriodicSummaries
 from .trajectory_transforms import (GAE, MergeTimeBatch, NormalizeAdvantages, policy_device,
                                     to_device)
@@ -44,7 +45,7 @@ class TransformInteractions(RunnerWrapper):
     self.lazy_upload = lazy_upload
 
   def _densify(self, key, val, device):
-    if isinstance(val, (torch.Tensor, HostColumn)):
+    if isinstance(val, (torch.Tensor, HostColumn, RowSelection)):
       return val
     try:
       arr = np.asarray(val)
@@ -73,24 +74,33 @@ def _row_bytes(t):
   return (t[0].numel() * t.element_size()) if t.shape[0] > 0 else 0
 
 
-def gather_minibatch(interactions, perm, start, count, host_perm=None, perm_ready=None):
+def gather_minibatch(interactions, perm, start, count, host_perm=None, perm_ready=None,
+                     fused_gather=False):
   """dict of rows perm[start:start+count] of every array in `interactions`.
 
   Wide columns (frame stacks) use the TMA row gather, all narrow columns share one launch
   which also reduces the float64 moments of `advantages` (attached as `_derl_moments`).
+  fused_gather: a resident `observations` column is handed on as a `RowSelection` (source +
+  row indices) for the network's stem kernels to read in place instead of being copied.
   """
   out, narrow = {}, []
   for key, val in interactions.items():
     if key == "state":
       out[key] = val
     elif isinstance(val, HostColumn):
-      out[key] = val.gather(perm, start, count, perm_ready)
+      if fused_gather and key == "observations" and val.complete:
+        out[key] = RowSelection(val.resident, perm, start, count)
+      else:
+        out[key] = val.gather(perm, start, count, perm_ready)
     elif isinstance(val, torch.Tensor):
       if not val.is_cuda:
         raise TypeError(f"interactions['{key}'] is a CPU tensor; the rollout must be resident "
                         "on the GPU (derl_b200 has no host gather path)")
       if _row_bytes(val) >= WIDE_ROW_BYTES:
-        out[key] = _K.gather_rows(val, perm, start, count)
+        if fused_gather and key == "observations" and val.is_contiguous():
+          out[key] = RowSelection(val, perm, start, count)
+        else:
+          out[key] = _K.gather_rows(val, perm, start, count)
       else:
         narrow.append(key)
     else:  # host object arrays (infos): plain NumPy fancy index with the same rows
@@ -116,11 +126,13 @@ def gather_minibatch(interactions, perm, start, count, host_perm=None, perm_read
 class IterateWithMinibatches(RunnerWrapper):
   """Iterates over interactions with minibatches for a given number of epochs."""
 
-  def __init__(self, runner, num_epochs=3, num_minibatches=4, shuffle_before_epoch=True):
+  def __init__(self, runner, num_epochs=3, num_minibatches=4, shuffle_before_epoch=True,
+               fused_gather=False):
     super().__init__(runner)
     self.num_epochs = num_epochs
     self.num_minibatches = num_minibatches
     self.shuffle_before_epoch = shuffle_before_epoch
+    self.fused_gather = fused_gather   # extension: see runners/row_selection.py
 
   @staticmethod
   def _sample_size(interactions):
@@ -170,10 +182,11 @@ class IterateWithMinibatches(RunnerWrapper):
         for start in range(0, size, mbsize):
           count = min(start + mbsize, size) - start
           yield gather_minibatch(interactions, perm, start, count, host_perm=order,
-                                 perm_ready=perm_ready)
+                                 perm_ready=perm_ready, fused_gather=self.fused_gather)
 
 
-def ppo_runner_wrap(runner, gamma=0.99, lambda_=0.95, num_epochs=3, num_minibatches=4):
+def ppo_runner_wrap(runner, gamma=0.99, lambda_=0.95, num_epochs=3, num_minibatches=4,
+                    fused_gather=False):
   """Wraps a rollout source for PPO: [GAE, MergeTimeBatch?] -> minibatches -> normalise
   (reference :65-75; MergeTimeBatch only for non-recurrent policies on batched envs)."""
   env, policy = runner.env, runner.policy
@@ -181,7 +194,7 @@ def ppo_runner_wrap(runner, gamma=0.99, lambda_=0.95, num_epochs=3, num_minibatc
   if not policy.is_recurrent() and getattr(env.unwrapped, "nenvs", None):
     transforms.append(MergeTimeBatch())
   runner = TransformInteractions(runner, transforms)
-  runner = IterateWithMinibatches(runner, num_epochs, num_minibatches)
+  runner = IterateWithMinibatches(runner, num_epochs, num_minibatches, fused_gather=fused_gather)
   return TransformInteractions(runner, [NormalizeAdvantages()])
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DERL_B200_ABI_VERSION 1
+#define DERL_B200_ABI_VERSION 2
 
 enum {
   DERL_OK = 0,
@@ -239,11 +239,17 @@ int derl_b200_space_to_depth(const void* src_dev, int64_t batch, int64_t height,
  *   out_block 1: out [batch, 20, 20, 32] channels-last;
  *   out_block 2: out [batch, 10, 10, 128], the space-to-depth(2) arrangement of the same
  *                activation (what derl_b200_space_to_depth would produce from it);
- *   out_dtype DERL_DTYPE_F32 or DERL_DTYPE_BF16.
+ *   out_dtype DERL_DTYPE_F32 or DERL_DTYPE_BF16;
+ *   rows_dev  NULL, or `batch` int64 row indices into frames_dev: frame i of the batch is
+ *             frames_dev[rows_dev[i]].  This fuses the minibatch gather of
+ *             IterateWithMinibatches (derl/runners/onpolicy.py:44-49,57-62) into the layer
+ *             (SURVEY §8f rank 2): the kernel pulls each 28 224-byte row straight out of the
+ *             resident rollout and the minibatch's observations are never materialised.
+ *             Indices are trusted (validate the permutation once, when it is uploaded).
  */
-int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const float* weight_dev,
-                             const float* bias_dev, void* out_dev, int out_dtype, int out_block,
-                             void* stream);
+int derl_b200_stem_conv_relu(const uint8_t* frames_dev, const int64_t* rows_dev, int64_t batch,
+                             const float* weight_dev, const float* bias_dev, void* out_dev,
+                             int out_dtype, int out_block, void* stream);
 
 /* ------------------------------------------------------------------ K7: stem backward from uint8 frames
  * Backward of the same layer (ReLU mask, bias gradient and weight gradient of
@@ -254,11 +260,13 @@ int derl_b200_stem_conv_relu(const uint8_t* frames_dev, int64_t batch, const flo
  *   frames [batch, 84, 84, 4] uint8; grad_out, out: float32 [batch, 400, 32] tiles of the
  *   activation gradient / activation, pixels in plain (oy*20 + ox) order (blocked = 0) or in the
  *   space-to-depth(2) order K6 emits with out_block = 2 (blocked = 1);
- *   grad_weight [32, 4, 8, 8] float32, grad_bias [32] float32 (overwritten).
+ *   grad_weight [32, 4, 8, 8] float32, grad_bias [32] float32 (overwritten);
+ *   rows_dev as in derl_b200_stem_conv_relu (NULL, or the fused gather's row indices).
  *   workspace >= derl_b200_stem_backward_workspace_bytes().  Deterministic. */
 size_t derl_b200_stem_backward_workspace_bytes(void);
-int derl_b200_stem_backward(const uint8_t* frames_dev, int64_t batch, const float* grad_out_dev,
-                            const float* out_dev, int blocked, float* grad_weight_dev,
+int derl_b200_stem_backward(const uint8_t* frames_dev, const int64_t* rows_dev, int64_t batch,
+                            const float* grad_out_dev, const float* out_dev, int blocked,
+                            float* grad_weight_dev,
                             float* grad_bias_dev, void* workspace_dev, size_t workspace_bytes,
                             void* stream);
 

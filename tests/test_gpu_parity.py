@@ -768,6 +768,104 @@ def test_stem_backward_kernel_vs_float32_autograd(blocked):
   torch.backends.cudnn.allow_tf32 = True
 
 
+def test_stem_kernels_with_fused_row_gather_are_bit_identical():
+  """K6 / K7 with `rows`: frame i of the batch is source[rows[i]], pulled straight out of the
+  resident rollout.  Same bytes in, deterministic kernels: bit-identical to
+  running them on the materialised gather, for both output layouts, with repeated rows."""
+  gen = torch.Generator(device=DEV).manual_seed(33)
+  weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.05
+  bias = torch.randn(32, device=DEV, generator=gen) * 0.1
+  source = torch.randint(0, 256, (97, 84, 84, 4), device=DEV, dtype=torch.uint8, generator=gen)
+  for count in (1, 5, 300):   # 300 > 97: rows repeat; > 296 CTAs of K7: second frames per CTA
+    rows = torch.randint(0, 97, (count,), device=DEV, generator=gen)
+    dense = source[rows]
+    for blk in (1, 2):
+      for dtype in (torch.float32, torch.bfloat16):
+        assert torch.equal(K.stem_conv_relu(source, weight, bias, dtype, blk, rows),
+                           K.stem_conv_relu(dense, weight, bias, dtype, blk))
+      out = K.stem_conv_relu(dense, weight, bias, torch.float32, blk).permute(0, 3, 1, 2)
+      grad = (torch.randn(out.shape, device=DEV, generator=gen) * 1e-3).contiguous(
+          memory_format=torch.channels_last)
+      want = K.stem_backward(dense, grad, out, blk == 2)
+      got = K.stem_backward(source, grad, out, blk == 2, rows)
+      assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+  with pytest.raises(ValueError, match="rows"):
+    K.stem_conv_relu(source, weight, bias, torch.float32, 1, rows.int())
+
+
+def test_fused_gather_minibatches_and_update_match_the_materialised_pipeline():
+  """IterateWithMinibatches(fused_gather=True) hands `observations` on as a RowSelection; the
+  NatureCNN stem reads the rollout rows in place.  Minibatch contents (materialised on demand),
+  loss and every parameter gradient equal the materialised pipeline's; Trainer's micro-batch
+  row slicing stays lazy; paths without the fused stem fall back to the materialised tensor."""
+  from derl_b200.runners.row_selection import RowSelection
+  nsteps, nenvs, nact = 12, 6, 4
+  torch.manual_seed(1)
+  policy = d.ActorCriticPolicy(d.NatureCNNModel([nact, 1]))
+  torch.backends.cudnn.deterministic = True
+  make_source = lambda: d.SyntheticRolloutRunner(policy, "atari", nenvs=nenvs, horizon=nsteps,
+                                                 seed=3, nactions=nact)
+  rollout = make_source().rollout()
+
+  def run(fused):
+    runner = d.ppo_runner_wrap(make_source(), num_epochs=2, num_minibatches=3, fused_gather=fused)
+    np.random.seed(7)
+    loss_fn = d.PPOLoss(policy, cliprange=0.1)
+    out = []
+    it = runner.run()
+    for _ in range(6):
+      batch = next(it)
+      policy.model.zero_grad()
+      loss = loss_fn(batch)
+      loss.backward()
+      out.append((batch, loss.detach().clone(), [p.grad.clone() for p in policy.model.parameters()]))
+    return out
+
+  eager, fused = run(False), run(True)
+  for (be, le, ge), (bf, lf, gf) in zip(eager, fused):
+    assert isinstance(bf["observations"], RowSelection) and isinstance(be["observations"], torch.Tensor)
+    assert bf["observations"].shape == be["observations"].shape
+    assert torch.equal(bf["observations"].materialize(), be["observations"])
+    assert torch.equal(bf["observations"][3:20].materialize(), be["observations"][3:20])
+    assert torch.equal(bf["observations"][5], be["observations"][5])
+    for key in be:
+      if key not in ("observations", "state"):
+        assert torch.equal(bf[key], be[key]), key
+    assert torch.equal(lf, le)
+    for a, b in zip(gf, ge):
+      assert torch.equal(a, b)
+  # micro-batched Trainer: row chunks of a RowSelection are RowSelections; same update
+  params0 = [p.detach().clone() for p in policy.model.parameters()]
+  finals = []
+  for fused_flag in (False, True):
+    with torch.no_grad():
+      for p, p0 in zip(policy.model.parameters(), params0):
+        p.copy_(p0)
+    runner = d.ppo_runner_wrap(make_source(), num_epochs=1, num_minibatches=2,
+                               fused_gather=fused_flag)
+    np.random.seed(9)
+    optimizer = torch.optim.SGD(policy.model.parameters(), lr=1e-3)
+    alg = d.PPO(runner, d.Trainer(optimizer, max_grad_norm=0.5, micro_batch=16), cliprange=0.1)
+    it = runner.run()
+    losses = [alg.step(next(it)) for _ in range(2)]
+    finals.append((torch.stack(losses), [p.detach().clone() for p in policy.model.parameters()]))
+  assert torch.equal(finals[0][0], finals[1][0])
+  for a, b in zip(finals[0][1], finals[1][1]):
+    assert torch.equal(a, b)
+  # strict-fp32 network (no K6/K7): the selection is materialised for the library stem
+  torch.backends.cudnn.allow_tf32 = False
+  sel = RowSelection(rollout["observations"].reshape(-1, 84, 84, 4),
+                     torch.randperm(nsteps * nenvs, device=DEV), 10, 17)
+  with torch.no_grad():
+    a = policy.model(sel)
+    b = policy.model(sel.materialize())
+  torch.backends.cudnn.allow_tf32 = True
+  torch.backends.cudnn.deterministic = False
+  assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+  with pytest.raises(ValueError):
+    RowSelection(sel.source, sel.perm, 70, 5)
+
+
 def test_stem_autograd_matches_cudnn_path():
   """NatureCNN with the K6 stem (TF32 allowed) vs the cuDNN stem: outputs and all parameter
   gradients agree to TF32-level tolerance; the stem weight gradient lands in [32,4,8,8] layout."""
