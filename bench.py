@@ -412,6 +412,12 @@ def run_ours(args, rank, world, local):
               "ppo_loss_categorical": (8 * args.nactions + 32) * min(args.micro_batch, mb_rows),
               "gather_columns": (8 + 2 * (8 + 4 + 4 + 4 + 4 + 4 + 1)) * mb_rows,
               "normalize": 8.0 * mb_rows}
+  if args.net == "tf32":   # stem kernels per micro-batch chunk (algorithmic bytes)
+    chunk = min(args.micro_batch, mb_rows)
+    per_elem["stem_conv_relu"] = (OBS_ROW_BYTES + 400 * 32 * 4.0) * chunk
+    per_elem["stem_backward"] = (OBS_ROW_BYTES + 2 * 400 * 32 * 4.0) * chunk
+    # K5 serves the 64x9x9 and 64x7x7 activations in turn: mean bytes of the two launches
+    per_elem["relu_bwd_bias"] = 12.0 * chunk * 64 * (81 + 49) / 2
   for name, (n, ms) in ktimes.items():
     entry = {"launches": n, "mean_ms": ms}
     if name in per_elem:
