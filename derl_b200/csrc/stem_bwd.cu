@@ -22,7 +22,8 @@
 //   mask + quantise, MMA) back to back and the SM overlaps one CTA's ALU phases with the other's
 //   tensor phase.  The frame arrives by a TMA bulk copy; the gradient and activation tiles are
 //   read with coalesced streaming loads straight into registers (one channel per lane), issued
-//   before the transpose so that they land while it runs.  Warp w owns quadrant w/2 and 32 taps.
+//   before the transpose so that they land while it runs.  Warp w owns kernel rows 4 (w / 4) .. + 3
+//   and frame channel w % 4 for both column halves (which share their Zt words, one byte apart).
 // Per-CTA partial sums are reduced (fixed order) and re-indexed to [32, 4, 8, 8] by a second
 // small kernel.
 #include "common.cuh"
@@ -41,7 +42,6 @@ constexpr int kGqPlane = kGroups * kCh * 16;  // Gq[plane][group][channel][4 qua
 // of equal c and equal (i, j) parity x 4 words) both touch every bank once.
 constexpr int kZtRow = 24, kZtTap = 520;
 constexpr int kWarps = 8, kThreads = kWarps * 32, kCtasPerSm = 2;
-constexpr int kNT = 4;                        // n8 tap tiles per warp (2 warps per quadrant)
 constexpr int kPartial = 4 * 64 * kCh;        // floats of one CTA's weight partial
 
 struct BwdSmem {
@@ -79,8 +79,7 @@ __device__ __forceinline__ int tile_pixel(int oy, int ox, int blocked) {
 __device__ __forceinline__ void quantise(float x, unsigned* b1, unsigned* b2) {
   const float m1 = x + 12582912.f;
   *b1 = __float_as_uint(m1);
-  const float r = (x - (m1 - 12582912.f)) * 254.f;
-  *b2 = __float_as_uint(r + 12582912.f);
+  *b2 = __float_as_uint(__fmaf_rn(x - (m1 - 12582912.f), 254.f, 12582912.f));
 }
 
 // low bytes of four words -> one word
@@ -138,21 +137,25 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
   __syncthreads();
 
   // ---- loop-invariant roles
-  const int quadrant = warp >> 1;                 // (a, b) = (quadrant >> 1, quadrant & 1)
-  const int qa = quadrant >> 1, qb = quadrant & 1;
-  const int ntile0 = (warp & 1) * kNT;            // n-tile nt: channel nt >> 1, (i, j) parity nt & 1
+  // MMA role: warp = (qa, c): kernel rows 4 qa .. 4 qa + 3, frame channel c, BOTH column halves
+  // qb = 0, 1 (they read the same Zt words, one byte apart) and both (i, j) parities:
+  // acc[m][n][qb] is n-tile nt = 2 c + n (channel nt >> 1, (i, j) parity nt & 1) of quadrant (qa, qb)
+  const int qa = warp >> 2;
+  const int ntile0 = (warp & 3) * 2;
   // mask / quantiser role: lane = channel; warp `sub` owns groups sub, sub + 8, sub + 16 (12 quads)
   // and, for sub < 4, quad 96 + sub of the last group
   const int ch = lane, sub = warp;
   const bool extra = sub < 4;
 
-  float wsum[2][kNT][4];                          // [m-tile][n-tile][c-frag] fp32 running sums
+  float wsum[2][2][2][4];                         // [m-tile][n-tile][qb][c-frag] fp32 running sums
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int n = 0; n < kNT; ++n)
+    for (int n = 0; n < 2; ++n)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) wsum[m][n][k] = 0.f;
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wsum[m][n][q][k] = 0.f;
   float bsum = 0.f;
 
   int it = 0;
@@ -284,36 +287,36 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
     }
     __syncthreads();   // Zt, Gq and scale complete
 
-    // ---- (4) MMAs: acc[m][n][plane] over 13 k32 steps (8 quads each)
-    int acc[2][kNT][2][4];
+    // ---- (4) MMAs: acc[m][n][qb][plane] over 13 k32 steps (8 quads each)
+    int acc[2][2][2][2][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int n = 0; n < kNT; ++n)
+      for (int n = 0; n < 2; ++n)
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[m][n][p][k] = 0;
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[m][n][q][p][k] = 0;
 
 #pragma unroll 1
     for (int s = 0; s < kSteps; ++s) {
       const int quad0 = 8 * s + t, quad1 = quad0 + 4;       // this lane's two quads of the step
-      // byte offsets of the two quads inside a Zt plane, shifted by this warp's quadrant
-      const int off0 = qzt[quad0] + qa * kZtRow + qb, off1 = qzt[quad1] + qa * kZtRow + qb;
-      unsigned b[kNT][2];
+      // byte offsets of the two quads inside a Zt plane, shifted by this warp's kernel-row half
+      const int off0 = qzt[quad0] + qa * kZtRow, off1 = qzt[quad1] + qa * kZtRow;
+      unsigned b[2][2][2];                                   // [n][qb][b0, b1]
 #pragma unroll
-      for (int n = 0; n < kNT; ++n) {
+      for (int n = 0; n < 2; ++n) {
         const int nt = ntile0 + n;
         const uint8_t* plane = zt + ((nt >> 1) * 16 + 2 * g + (nt & 1)) * kZtTap;
-        if (qb == 0) {   // aligned
-          b[n][0] = *reinterpret_cast<const unsigned*>(plane + off0);
-          b[n][1] = *reinterpret_cast<const unsigned*>(plane + off1);
-        } else {         // bytes 1..4 of two aligned words
-          const unsigned* p0 = reinterpret_cast<const unsigned*>(plane + off0 - 1);
-          const unsigned* p1 = reinterpret_cast<const unsigned*>(plane + off1 - 1);
-          b[n][0] = __byte_perm(p0[0], p0[1], 0x4321);
-          b[n][1] = __byte_perm(p1[0], p1[1], 0x4321);
-        }
+        const unsigned* p0 = reinterpret_cast<const unsigned*>(plane + off0);
+        const unsigned* p1 = reinterpret_cast<const unsigned*>(plane + off1);
+        const unsigned w00 = p0[0], w01 = p0[1], w10 = p1[0], w11 = p1[1];
+        b[n][0][0] = w00;                                    // qb = 0: the aligned word
+        b[n][0][1] = w10;
+        b[n][1][0] = __byte_perm(w00, w01, 0x4321);          // qb = 1: bytes 1..4
+        b[n][1][1] = __byte_perm(w10, w11, 0x4321);
       }
 #pragma unroll
       for (int m = 0; m < 2; ++m)
@@ -327,7 +330,9 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
           a[2] = *reinterpret_cast<const unsigned*>(row + kCh * 16);
           a[3] = *reinterpret_cast<const unsigned*>(row + (kCh + 8) * 16);
 #pragma unroll
-          for (int n = 0; n < kNT; ++n) mma_s8u8(acc[m][n][p], a, b[n][0], b[n][1]);
+          for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) mma_s8u8(acc[m][n][q][p], a, b[n][q][0], b[n][q][1]);
         }
     }
 
@@ -336,31 +341,35 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
     for (int m = 0; m < 2; ++m) {
       const float s_lo = scale[16 * m + g], s_hi = scale[16 * m + g + 8];
 #pragma unroll
-      for (int n = 0; n < kNT; ++n) {
+      for (int n = 0; n < 2; ++n)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float x = (float)acc[m][n][0][k] + (float)acc[m][n][1][k] * (1.f / 254.f);
-          wsum[m][n][k] += x * (k < 2 ? s_lo : s_hi);
-        }
-      }
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x = (float)acc[m][n][q][0][k] + (float)acc[m][n][q][1][k] * (1.f / 254.f);
+            wsum[m][n][q][k] += x * (k < 2 ? s_lo : s_hi);
+          }
     }
     __syncthreads();   // everyone is done with Zt / Gq / scale / red before the next frame
   }
 
   // ---- per-CTA partials: partial_w[cta][quadrant][tap][channel], partial_b[cta][channel]
-  float* pw = partial_w + (size_t)blockIdx.x * kPartial + (size_t)quadrant * (64 * kCh);
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int q = 0; q < 2; ++q) {
+    float* pw = partial_w + (size_t)blockIdx.x * kPartial + (size_t)(qa * 2 + q) * (64 * kCh);
 #pragma unroll
-    for (int n = 0; n < kNT; ++n) {
-      // D column col (= 2t, 2t + 1) of n-tile nt is (i, j) = 2 col + (nt & 1), channel nt >> 1
-      const int nt = ntile0 + n, c_lo = 16 * m + g;
-      const int tap = ((4 * t + (nt & 1)) << 2) + (nt >> 1);   // (i*4+j)*4 + c of column 2t
-      pw[tap * kCh + c_lo] = wsum[m][n][0];
-      pw[(tap + 8) * kCh + c_lo] = wsum[m][n][1];
-      pw[tap * kCh + c_lo + 8] = wsum[m][n][2];
-      pw[(tap + 8) * kCh + c_lo + 8] = wsum[m][n][3];
-    }
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        // D column col (= 2t, 2t + 1) of n-tile nt is (i, j) = 2 col + (nt & 1), channel nt >> 1
+        const int nt = ntile0 + n, c_lo = 16 * m + g;
+        const int tap = ((4 * t + (nt & 1)) << 2) + (nt >> 1);   // (i*4+j)*4 + c of column 2t
+        pw[tap * kCh + c_lo] = wsum[m][n][q][0];
+        pw[(tap + 8) * kCh + c_lo] = wsum[m][n][q][1];
+        pw[tap * kCh + c_lo + 8] = wsum[m][n][q][2];
+        pw[(tap + 8) * kCh + c_lo + 8] = wsum[m][n][q][3];
+      }
+  }
   __syncthreads();
   red[sub * kCh + ch] = bsum;
   __syncthreads();
