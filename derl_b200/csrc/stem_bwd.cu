@@ -67,6 +67,15 @@ __device__ __forceinline__ void mma_s8u8(int (&d)[4], const unsigned (&a)[4], un
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// One m16 x k32 int8 A fragment = four 8-row x 16-byte matrices: lane l supplies the address of row
+// l % 8 of matrix l / 8 and receives, per matrix, bytes 4 (l % 4) .. + 3 of row l / 4 — exactly the
+// a0..a3 registers of mma.m16n8k32 when the matrices are (rows 0-7 | rows 8-15) x (k 0-15 | k 16-31).
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&a)[4], unsigned smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(smem_addr));
+}
+
 // index of output pixel (oy, ox) inside a frame's [400 x 32] tile, in units of pixels
 __device__ __forceinline__ int tile_pixel(int oy, int ox, int blocked) {
   if (blocked) return (((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
@@ -142,6 +151,10 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
   // acc[m][n][qb] is n-tile nt = 2 c + n (channel nt >> 1, (i, j) parity nt & 1) of quadrant (qa, qb)
   const int qa = warp >> 2;
   const int ntile0 = (warp & 3) * 2;
+  // A fragments by ldmatrix: lane -> (matrix = lane / 8, row = lane % 8); matrices 0/1 are channels
+  // +0..7 / +8..15 of group 2s, matrices 2/3 the same channels of group 2s + 1 (16-byte rows of Gq)
+  const unsigned gq_lane = (unsigned)__cvta_generic_to_shared(gq) +
+                           (((lane >> 4) * kCh + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
   // mask / quantiser role: lane = channel; warp `sub` owns groups sub, sub + 8, sub + 16 (12 quads)
   // and, for sub < 4, quad 96 + sub of the last group
   const int ch = lane, sub = warp;
@@ -323,12 +336,8 @@ stem_bwd_kernel(const uint8_t* __restrict__ frames, const long long* __restrict_
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           // quads 8s + t and 8s + 4 + t live in groups 2s and 2s + 1 at word t
-          const uint8_t* row = gq + p * kGqPlane + ((2 * s) * kCh + 16 * m + g) * 16 + 4 * t;
           unsigned a[4];
-          a[0] = *reinterpret_cast<const unsigned*>(row);
-          a[1] = *reinterpret_cast<const unsigned*>(row + 8 * 16);
-          a[2] = *reinterpret_cast<const unsigned*>(row + kCh * 16);
-          a[3] = *reinterpret_cast<const unsigned*>(row + (kCh + 8) * 16);
+          ldmatrix_x4(a, gq_lane + p * kGqPlane + ((2 * s) * kCh + 16 * m) * 16);
 #pragma unroll
           for (int n = 0; n < 2; ++n)
 #pragma unroll
