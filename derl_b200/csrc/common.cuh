@@ -187,6 +187,15 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
                : "memory");
 }
+// One m16 x k32 int8 A fragment = four 8-row x 16-byte matrices: lane l supplies the address of row
+// l % 8 of matrix l / 8 and receives, per matrix, bytes 4 (l % 4) .. + 3 of row l / 4 — exactly the
+// a0..a3 registers of mma.m16n8k32 when the matrices are (rows 0-7 | rows 8-15) x (k 0-15 | k 16-31).
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&a)[4], unsigned smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(smem_addr));
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

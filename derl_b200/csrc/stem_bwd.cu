@@ -67,15 +67,6 @@ __device__ __forceinline__ void mma_s8u8(int (&d)[4], const unsigned (&a)[4], un
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// One m16 x k32 int8 A fragment = four 8-row x 16-byte matrices: lane l supplies the address of row
-// l % 8 of matrix l / 8 and receives, per matrix, bytes 4 (l % 4) .. + 3 of row l / 4 — exactly the
-// a0..a3 registers of mma.m16n8k32 when the matrices are (rows 0-7 | rows 8-15) x (k 0-15 | k 16-31).
-__device__ __forceinline__ void ldmatrix_x4(unsigned (&a)[4], unsigned smem_addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-               : "r"(smem_addr));
-}
-
 // index of output pixel (oy, ox) inside a frame's [400 x 32] tile, in units of pixels
 __device__ __forceinline__ int tile_pixel(int oy, int ox, int blocked) {
   if (blocked) return (((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
