@@ -98,9 +98,12 @@ class _ConvBiasReLU(torch.autograd.Function):
 
 class _StemConvReLU(torch.autograd.Function):
   """The 8x8/4 stem + bias + ReLU straight from uint8 frames (derl_b200 K6) forward, optionally
-  emitting the space-to-depth(2) arrangement the next layer consumes; backward = K5 (ReLU mask +
-  bias gradient) and the weight gradient of the equivalent space-to-depth conv (K4 re-creates
-  the float frames only here, cuDNN wgrad), mapped back to [32, 4, 8, 8]."""
+  emitting the space-to-depth(2) arrangement the next layer consumes.  Backward: K7 (ReLU mask +
+  bias gradient + weight gradient in one INT8 tensor-core pass over the same uint8 frames) for
+  float32 activations; otherwise (bf16 autocast) K5 (ReLU mask + bias gradient) and the weight
+  gradient of the equivalent space-to-depth conv (K4 re-creates the float frames, cuDNN wgrad),
+  mapped back to [32, 4, 8, 8].  With `rows` both kernels read frames[rows] in place: the
+  minibatch gather fused into the layer (runners/row_selection.py)."""
 
   @staticmethod
   def forward(ctx, frames, weight, bias, dtype, out_block, rows=None):

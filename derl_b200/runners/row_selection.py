@@ -7,7 +7,8 @@ is a `RowSelection` instead: the NatureCNN stem kernels (K6 forward, K7 backward
 row indices and pull each 28 224-byte row straight out of the resident rollout (SURVEY §8f
 rank 2), so the minibatch copy — one write and one extra read of every frame — never happens.
 Anything else that touches the object gets the materialised tensor (`materialize()`, any
-index other than a contiguous row slice, `.to()`, `.clone()`, `.cpu()`).
+index other than a contiguous row slice, `.to()`, `.clone()`, `.cpu()`) — produced by the K2
+gather kernel, so on a host tensor it fails loudly like every other derl_b200 op.
 """
 import torch
 
@@ -20,8 +21,8 @@ class RowSelection:
   """`source[perm[start:start+count]]`, lazily."""
 
   def __init__(self, source, perm, start, count):
-    if not (isinstance(source, torch.Tensor) and source.is_cuda and source.is_contiguous()):
-      raise TypeError("RowSelection needs a contiguous CUDA tensor as its source")
+    if not (isinstance(source, torch.Tensor) and source.is_contiguous()):
+      raise TypeError("RowSelection needs a contiguous tensor as its source")
     if perm.dtype != torch.int64 or perm.dim() != 1 or perm.device != source.device:
       raise TypeError("RowSelection needs a 1-D int64 permutation on the source's device")
     start, count = int(start), int(count)
@@ -35,7 +36,7 @@ class RowSelection:
   ndim = property(lambda self: self.source.ndim)
   dtype = property(lambda self: self.source.dtype)
   device = property(lambda self: self.source.device)
-  is_cuda = property(lambda self: True)
+  is_cuda = property(lambda self: self.source.is_cuda)
 
   def dim(self):
     return self.source.ndim

@@ -27,6 +27,40 @@ def test_library_exports_every_declared_symbol():
   assert sorted(_lib.SIGNATURES) == names, "ctypes signature table out of sync with the header"
 
 
+def declared_prototypes():
+  """name -> list of C parameter declarations, parsed from the header."""
+  with open(os.path.join(REPO, "include", "derl_b200.h")) as f:
+    text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+  protos = {}
+  for ret, name, params in re.findall(r"\b([\w\s\*]+?)\b(derl_b200_\w+)\s*\(([^)]*)\)\s*;", text):
+    params = " ".join(params.split())
+    protos[name] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+  return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+  """Same arity and same argument classes (pointer / 64-bit / int / double / size_t) in the
+  ctypes table as in include/derl_b200.h: an ABI change must touch both (and ABI_VERSION)."""
+  def classify(decl):
+    if "*" in decl:
+      return ctypes.c_void_p
+    kind = decl.rsplit(" ", 1)[0].replace("const ", "").strip()
+    return {"int64_t": ctypes.c_int64, "int": ctypes.c_int, "double": ctypes.c_double,
+            "size_t": ctypes.c_size_t, "float": ctypes.c_float}[kind]
+  protos = declared_prototypes()
+  assert sorted(protos) == sorted(_lib.SIGNATURES)
+  for name, params in protos.items():
+    _, argtypes = _lib.SIGNATURES[name]
+    assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters"
+    for i, (decl, argtype) in enumerate(zip(params, argtypes)):
+      want = classify(decl)
+      same = argtype is want or (want is ctypes.c_void_p and argtype in (ctypes.c_void_p,
+                                                                        ctypes.c_char_p))
+      assert same, f"{name} argument {i} ({decl!r}): ctypes table says {argtype.__name__}"
+  with open(os.path.join(REPO, "include", "derl_b200.h")) as f:
+    assert f"#define DERL_B200_ABI_VERSION {_lib.ABI_VERSION}\n" in f.read()
+
+
 def test_abi_version_and_error_string():
   lib = _lib.load()
   assert lib.derl_b200_abi_version() == _lib.ABI_VERSION

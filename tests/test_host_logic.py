@@ -237,3 +237,31 @@ def test_env_runner_list_and_resident_modes_agree():
       def act(self, obs, **kw):
         return dict(values=np.zeros((4, 1), np.float32))
     next(d.EnvRunner(CountingEnv(), NoActions(), 2, 10).run())
+
+
+def test_row_selection_is_a_lazy_descriptor():
+  """RowSelection (fused minibatch gather, runners/row_selection.py): shape / slicing / row
+  indices are pure bookkeeping; materialising needs the CUDA gather kernel (no CPU path)."""
+  from derl_b200.runners.row_selection import RowSelection, dense
+  source = torch.arange(10 * 6, dtype=torch.uint8).reshape(10, 2, 3)
+  perm = torch.tensor([3, 1, 4, 1, 5, 9, 2, 6])
+  sel = RowSelection(source, perm, 2, 5)
+  assert sel.shape == (5, 2, 3) and len(sel) == 5 and sel.ndim == 3 and sel.dtype == torch.uint8
+  assert sel.size(0) == 5 and sel.dim() == 3 and sel.is_contiguous() and not sel.is_cuda
+  assert sel.rows.tolist() == [4, 1, 5, 9, 2]
+  assert sel[()] is sel
+  part = sel[1:4]
+  assert isinstance(part, RowSelection) and part.rows.tolist() == [1, 5, 9] and part.source is source
+  assert sel[3:].rows.tolist() == [9, 2] and len(sel[7:]) == 0
+  assert "perm[2:7]" in repr(sel)
+  with pytest.raises(NotImplementedError):   # gather_rows is registered for CUDA only
+    sel.materialize()
+  with pytest.raises(NotImplementedError):
+    sel[::2]
+  with pytest.raises(ValueError):
+    RowSelection(source, perm, 5, 4)
+  with pytest.raises(TypeError):
+    RowSelection(source, perm.int(), 0, 2)
+  with pytest.raises(TypeError):
+    RowSelection(source.permute(1, 0, 2), perm, 0, 2)
+  assert dense(source) is source
