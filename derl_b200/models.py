@@ -5,10 +5,13 @@ broadcast_inputs :141-163, NatureCNNModel :166-214, MLP :224-237, MuJoCoModel :2
 make_model :281-298.  Only the options PPO uses are carried (no noisy / dueling /
 distributional heads: those belong to DQN / SAC, outside the hot path).
 
-These layers are the one tensor-core consumer of the update and deliberately stay library
-calls (cuDNN conv / cuBLAS GEMM).  B200-specific choice: an NHWC uint8 frame stack viewed as
+The hidden conv / linear layers stay library calls (cuDNN / cuBLAS tensor-core kernels); the
+stem — the one layer that touches the uint8 frames — runs on derl_b200's own INT8 tensor-core
+kernels (K6 forward, K7 backward) whenever a reduced-precision tensor-core path is allowed
+(TF32 or autocast).  B200-specific choices around them: an NHWC uint8 frame stack viewed as
 NCHW *is* a channels_last tensor, so the trunk runs channels_last end to end and the
-reference's NCHW `.contiguous()` transpose copy (models.py:123) never happens.
+reference's NCHW `.contiguous()` transpose copy (models.py:123) never happens; strided convs
+with kernel = 2 x stride run as 2x2/1 convs on space-to-depth tensors.
 """
 import numpy as np
 import torch
