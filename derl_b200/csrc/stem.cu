@@ -52,7 +52,22 @@ __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float x,
 
 // frames [B,84,84,4] u8; weight [32,4,8,8] f32 (PyTorch conv layout); bias [32];
 // out [B,20,20,32] channels-last, or [B,10,10,128] when out_block == 2.
-constexpr int kI8Warps = 9, kI8Threads = kI8Warps * 32, kI8Tiles = 3, kPlanes = 2;
+// Tuning knobs (tools/tune_stem.py builds and times variants): warps x m16-tiles per warp must
+// cover the 25 tiles of a frame.
+#ifndef DERL_STEM_WARPS
+#define DERL_STEM_WARPS 9
+#endif
+#ifndef DERL_STEM_TILES
+#define DERL_STEM_TILES 3
+#endif
+#ifndef DERL_STEM_UNROLL
+#define DERL_STEM_UNROLL 8
+#endif
+#define DERL_STEM_PRAGMA_(x) _Pragma(#x)
+#define DERL_STEM_PRAGMA(x) DERL_STEM_PRAGMA_(x)
+constexpr int kI8Warps = DERL_STEM_WARPS, kI8Threads = kI8Warps * 32, kI8Tiles = DERL_STEM_TILES;
+constexpr int kPlanes = 2;
+static_assert(kI8Warps * kI8Tiles * 16 >= kOutHW * kOutHW, "tiles must cover the frame");
 
 struct StemI8Smem {
   static constexpr size_t raw_off = 0;                                  // [2][28224] u8
@@ -159,7 +174,7 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
 #pragma unroll
           for (int k = 0; k < 4; ++k) acc[m][n][p][k] = 0;
 
-#pragma unroll 2
+    DERL_STEM_PRAGMA(unroll DERL_STEM_UNROLL)
     for (int kh = 0; kh < 8; ++kh) {
       uint4 bq[4];
 #pragma unroll
