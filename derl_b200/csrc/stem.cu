@@ -63,6 +63,12 @@ __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float x,
 #ifndef DERL_STEM_UNROLL
 #define DERL_STEM_UNROLL 8
 #endif
+// 1: warps hand the frame buffer back through an `empty` mbarrier and run their epilogues
+// independently (tensor work of some warps overlaps the stores of others); 0: one
+// __syncthreads per frame keeps every warp in the same phase.
+#ifndef DERL_STEM_DECOUPLED
+#define DERL_STEM_DECOUPLED 1
+#endif
 #define DERL_STEM_PRAGMA_(x) _Pragma(#x)
 #define DERL_STEM_PRAGMA(x) DERL_STEM_PRAGMA_(x)
 constexpr int kI8Warps = DERL_STEM_WARPS, kI8Threads = kI8Warps * 32, kI8Tiles = DERL_STEM_TILES;
@@ -75,7 +81,7 @@ struct StemI8Smem {
   static constexpr size_t scale_off = w_off + 8 * 4 * 32 * 16;          // [32] float s
   static constexpr size_t bias_off = scale_off + kOutC * 4;
   static constexpr size_t bar_off = bias_off + kOutC * 4;
-  static constexpr size_t bytes = bar_off + 16;
+  static constexpr size_t bytes = bar_off + 32;                         // full[2], empty[2]
 };
 
 __device__ __forceinline__ void mma_u8s8(int (&d)[4], const unsigned (&a)[4], unsigned b0,
@@ -97,6 +103,7 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
   float* ssm = reinterpret_cast<float*>(smem + StemI8Smem::scale_off);
   float* bsm = reinterpret_cast<float*>(smem + StemI8Smem::bias_off);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + StemI8Smem::bar_off);
+  uint64_t* empty = full + 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
@@ -104,6 +111,8 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
+    mbar_init(&empty[0], kI8Warps);
+    mbar_init(&empty[1], kI8Warps);
     mbar_fence_init();
     for (int b = 0; b < 2; ++b) {
       if (first + b * stride < batch) {
@@ -194,13 +203,19 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
         }
       }
     }
-    __syncthreads();  // all warps are done with raw[buf]: refill it with the frame after next
-    if (tid == 0 && f + 2 * stride < batch) {
+    auto refill = [&]() {   // raw[buf] <- the frame after next
       mbar_expect_tx(&full[buf], kImgBytes);
       const long long i = f + 2 * stride;
       bulk_g2s(smem + StemI8Smem::raw_off + (size_t)buf * kImgBytes,
                frames + (rows ? __ldg(rows + i) : i) * kImgBytes, kImgBytes, &full[buf]);
-    }
+    };
+#if DERL_STEM_DECOUPLED
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);   // this warp is done reading raw[buf]
+#else
+    __syncthreads();  // all warps are done with raw[buf]
+    if (tid == 0 && f + 2 * stride < batch) refill();
+#endif
 
     OT* dst = out + f * (long long)(kPix * kOutC);
     const float inv255 = 1.0f / 255.0f, inv254 = 1.0f / 254.0f;
@@ -231,6 +246,14 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
         store2<OT>(dst + o1 + ch, y[2], y[3]);
       }
     }
+#if DERL_STEM_DECOUPLED
+    // producer: by the time warp 0 has stored its tiles the other warps have normally left the
+    // MMA loop of this frame; the copy then has the whole next frame's time to land
+    if (tid == 0 && f + 2 * stride < batch) {
+      mbar_wait(&empty[buf], (unsigned)((it >> 1) & 1));
+      refill();
+    }
+#endif
   }
 }
 
