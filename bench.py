@@ -406,7 +406,11 @@ def run_ours(args, rank, world, local):
     roofline = {"bound": "hbm", "kernel": "gather_rows_tma_kernel", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_kind, "bytes_per_launch": bytes_per_launch,
-                "launch_ms": ms, "launches_timed": n}
+                "launch_ms": ms, "launches_timed": n,
+                "note": "dominant kernel of the north-star data path (GAE -> gather -> loss); by "
+                        "time the largest derl_b200 kernels of the whole update are the network "
+                        "stem's (SURVEY 8f rank 2): see kernels.stem_backward / stem_conv_relu "
+                        "for their algorithmic GB/s and fraction of the same peak"}
   per_elem = {"gae": 17.0 * horizon * nenvs + 4 * nenvs,
               "frames_to_s2d": 5.0 * OBS_ROW_BYTES * min(args.micro_batch, mb_rows),
               "ppo_loss_categorical": (8 * args.nactions + 32) * min(args.micro_batch, mb_rows),
