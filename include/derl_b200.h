@@ -28,6 +28,7 @@
 extern "C" {
 #endif
 
+/* 2: derl_b200_stem_conv_relu / derl_b200_stem_backward gained `rows_dev` (fused minibatch gather). */
 #define DERL_B200_ABI_VERSION 2
 
 enum {
