@@ -12,8 +12,10 @@ namespace derl {
 // ---------------------------------------------------------------- host-side error plumbing
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t err, const char* what);
-int require_device();          // DERL_OK or DERL_E_NO_DEVICE (cached after first success)
-int sm_count();                // multiprocessor count of the current device (cached)
+int require_device();          // DERL_OK or DERL_E_NO_DEVICE for the CURRENT device (cached per device)
+int sm_count();                // multiprocessor count of the current device (cached per device)
+// raise a kernel's dynamic shared memory limit once per (device, kernel); DERL_OK or an error code
+int ensure_dynamic_smem(const void* func, int bytes);
 void count_launch(unsigned n = 1);
 
 #define DERL_CUDA(call)                                        \

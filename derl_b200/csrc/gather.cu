@@ -213,13 +213,7 @@ static int gather_rows_impl(const void* src, int64_t n_src_rows, int64_t row_byt
     const int cpr = (int)((row_bytes + kStageBytes - 1) / kStageBytes);
     // equal 16-byte-multiple chunks; the last one takes the remainder
     long long chunk = ((row_bytes + cpr - 1) / cpr + 15) & ~15ll;
-    static bool attr_set = false;
-    if (!attr_set) {
-      DERL_CUDA(cudaFuncSetAttribute(gather_rows_tma_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kGatherSmem));
-      attr_set = true;
-    }
+    if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(gather_rows_tma_kernel), (int)kGatherSmem)) return rc_attr;
     const long long units = count * cpr;
     long long grid = sm_count();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;

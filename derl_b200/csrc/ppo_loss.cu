@@ -356,12 +356,7 @@ int derl_b200_ppo_loss_categorical(const float* logits, int64_t B, int64_t A,
   cudaStream_t st = as_stream(stream);
   size_t smem = 0;
   const int R = pick_rows(A, 1, &smem);
-  static bool attr_set = false;  // once: not a stream operation, keep it out of graph captures
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_categorical_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_categorical_kernel), kMaxTileBytes)) return rc_attr;
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
   ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
       logits, (int)A, reinterpret_cast<const long long*>(actions), old_logp, adv, values, vtarg,
@@ -394,12 +389,7 @@ int derl_b200_ppo_loss_gaussian(const float* loc, const float* scale, int64_t B,
   cudaStream_t st = as_stream(stream);
   size_t smem = 0;
   const int R = pick_rows(D, 3, &smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_gaussian_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_gaussian_kernel), kMaxTileBytes)) return rc_attr;
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
   ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
       loc, scale, (int)D, actions, old_logp, adv, values, vtarg, vold,
@@ -431,12 +421,7 @@ int derl_b200_a2c_loss_categorical(const float* logits, int64_t B, int64_t A,
   cudaStream_t st = as_stream(stream);
   size_t smem = 0;
   const int R = pick_rows(A, 1, &smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_categorical_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_categorical_kernel), kMaxTileBytes)) return rc_attr;
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
   ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
       logits, (int)A, reinterpret_cast<const long long*>(actions), nullptr, adv, values, vtarg,
@@ -466,12 +451,7 @@ int derl_b200_a2c_loss_gaussian(const float* loc, const float* scale, int64_t B,
   cudaStream_t st = as_stream(stream);
   size_t smem = 0;
   const int R = pick_rows(D, 3, &smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(ppo_loss_gaussian_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTileBytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_gaussian_kernel), kMaxTileBytes)) return rc_attr;
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
   ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
       loc, scale, (int)D, actions, nullptr, adv, values, vtarg, nullptr,

@@ -261,12 +261,7 @@ template <typename OT>
 int launch(const uint8_t* frames, const long long* rows, const float* weight, const float* bias,
            void* out, long long batch, int out_block, cudaStream_t st) {
   auto kern = stem_conv_relu_i8_kernel<OT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)StemI8Smem::bytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)StemI8Smem::bytes)) return rc_attr;
   long long grid = batch;
   const long long cap = (long long)sm_count() * 2;
   if (grid > cap) grid = cap;

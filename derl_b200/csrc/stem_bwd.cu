@@ -441,12 +441,7 @@ extern "C" int derl_b200_stem_backward(const uint8_t* frames, const int64_t* row
     return DERL_E_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DERL_CUDA(cudaFuncSetAttribute(stem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)BwdSmem::bytes));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(stem_bwd_kernel), (int)BwdSmem::bytes)) return rc_attr;
   const long long max_grid = (long long)kCtasPerSm * sm_count();
   long long grid = batch < max_grid ? batch : max_grid;
   float* partial_w = reinterpret_cast<float*>(workspace);

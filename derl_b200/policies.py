@@ -88,6 +88,18 @@ class ActorCriticPolicy(Policy):
     if state is not None:
       raise NotImplementedError()
     observations = inputs["observations"] if training else inputs
+    if training:
+      return self._heads(observations)
+    # rollout mode: nothing differentiates through these outputs (the reference detaches them on
+    # the way to NumPy, policies.py:76-80), so no graph — frames and activations are not kept
+    # alive for a backward that never comes
+    with torch.no_grad():
+      out = self._heads(observations)
+      actions = out["distribution"].sample()
+      log_prob = out["distribution"].log_prob(actions)
+    return {"actions": _np(actions), "log_prob": _np(log_prob), "values": _np(out["values"])}
+
+  def _heads(self, observations):
     *dist_inputs, values = self.model(observations)
     if self.distribution is not None:
       distribution = self.distribution(*dist_inputs)
@@ -100,9 +112,4 @@ class ActorCriticPolicy(Policy):
                        "outputs to create a distribution, "
                        "expected a single output for categorical "
                        "and two outputs for normal distributions")
-    if training:
-      return {"distribution": distribution, "values": values}
-    with torch.no_grad():
-      actions = distribution.sample()
-      log_prob = distribution.log_prob(actions)
-    return {"actions": _np(actions), "log_prob": _np(log_prob), "values": _np(values)}
+    return {"distribution": distribution, "values": values}

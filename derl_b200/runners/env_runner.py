@@ -18,23 +18,49 @@ _FORWARDED = frozenset(("env", "policy", "horizon", "nsteps", "step_count", "nen
 class _ResidentRollout:
   """Preallocated [horizon, ...] tensors on `device`, filled one step at a time
   (SURVEY.md §8f rank 3): the rollout is born in HBM instead of being stacked from T host
-  lists (`np.asarray`, derl/runners/onpolicy.py:20-27) and uploaded afterwards."""
+  lists (`np.asarray`, derl/runners/onpolicy.py:20-27) and uploaded afterwards.
+
+  On a CUDA device every column has a PINNED host mirror of the same shape: a step's value is
+  written into its mirror row (a host memcpy) and that row is handed to an asynchronous H2D copy —
+  a copy from pageable memory would block the host for every step.  A mirror row is rewritten
+  one rollout later at the earliest; `begin()` waits for the previous rollout's copies first."""
 
   def __init__(self, horizon, device):
     self.horizon, self.device = horizon, torch.device(device)
+    self.buffers, self.mirrors = {}, {}
+    self.pinned = self.device.type == "cuda"
+    self.drained = None
+
+  def begin(self):
+    """Fresh device tensors for a new rollout (the previous ones now belong to the consumer)."""
+    if self.drained is not None:
+      self.drained.synchronize()
+      self.drained = None
     self.buffers = {}
 
   def put(self, key, step, value):
     arr = np.asarray(value)
     if arr.dtype == object or arr.dtype.kind in "USV":
       return False
+    host = torch.from_numpy(np.ascontiguousarray(arr))
     buf = self.buffers.get(key)
-    if buf is None or buf.shape[1:] != arr.shape or buf.dtype != torch.from_numpy(arr[None]).dtype:
-      buf = self.buffers[key] = torch.empty((self.horizon,) + arr.shape,
-                                            dtype=torch.from_numpy(arr[None]).dtype,
+    if buf is None or buf.shape[1:] != host.shape or buf.dtype != host.dtype:
+      buf = self.buffers[key] = torch.empty((self.horizon,) + tuple(host.shape), dtype=host.dtype,
                                             device=self.device)
-    buf[step].copy_(torch.from_numpy(np.ascontiguousarray(arr)), non_blocking=True)
+    if not self.pinned:
+      buf[step].copy_(host)
+      return True
+    mirror = self.mirrors.get(key)
+    if mirror is None or mirror.shape != buf.shape or mirror.dtype != buf.dtype:
+      mirror = self.mirrors[key] = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+    mirror[step].copy_(host)
+    buf[step].copy_(mirror[step], non_blocking=True)
     return True
+
+  def end(self):
+    if self.pinned:
+      self.drained = torch.cuda.Event()
+      self.drained.record(torch.cuda.current_stream(self.device))
 
 
 class EnvRunner:
@@ -42,7 +68,11 @@ class EnvRunner:
 
   `resident_device` (extension, default None = reference behaviour): write every numeric
   per-step value straight into preallocated device tensors; `next_observations` is then not
-  collected (nothing on the PPO path reads it) and `infos` stays a host list.
+  collected (nothing on the PPO path reads it) and `infos` stays a host list.  In that mode the
+  rollout also carries `state["latest_values"]`: the critic's value of the final observation,
+  taken from the forward pass this runner makes on it right after the last step (the same batch
+  a GAE bootstrap would evaluate, derl/runners/trajectory_transforms.py:47-50) and kept on the
+  device, so `derl_b200.GAE` does not run a second forward or a host round trip for it.
   """
 
   def __init__(self, env, policy, horizon, nsteps=None, time_limit=None, resident_device=None):
@@ -55,6 +85,7 @@ class EnvRunner:
     self.time_limit = time_limit
     self.step_count = 0
     self.episode_length = 0
+    self._resident = None
 
   @property
   def nenvs(self):
@@ -74,7 +105,10 @@ class EnvRunner:
       rollout = {}
       resident = None
       if self.resident_device is not None:
-        resident = _ResidentRollout(self.horizon, self.resident_device)
+        if self._resident is None:
+          self._resident = _ResidentRollout(self.horizon, self.resident_device)
+        resident = self._resident
+        resident.begin()
 
       def put(key, val, step):
         if resident is not None and key == "next_observations":
@@ -105,6 +139,12 @@ class EnvRunner:
         else:
           obs = next_obs
       rollout["state"] = dict(latest_observations=obs)
+      if resident is not None:
+        resident.end()
+        values = self.policy.act(obs).get("values")
+        if values is not None:
+          rollout["state"]["latest_values"] = torch.as_tensor(np.asarray(values)).to(
+              resident.device)
       self.step_count += self.horizon * (self.nenvs or 1)
       yield rollout
 

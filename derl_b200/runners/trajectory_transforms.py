@@ -63,6 +63,8 @@ class GAE:
   def bootstrap_value(self, trajectory):
     """policy.act(latest_observations)["values"], as the reference asks for it (:47-50)."""
     state = trajectory["state"]
+    if state.get("latest_values") is not None:   # EnvRunner(resident_device=): already evaluated
+      return state["latest_values"]
     return self.policy.act(state["latest_observations"], state=state.get("policy_state", None),
                            update_state=False)["values"]
 
@@ -163,11 +165,32 @@ class NormalizeAdvantages:
 
 
 class Take:
-  """Keeps data only from the given indices along `axis` for every key but "state" (:95-103)."""
+  """Keeps data only from the given indices along `axis` for every key but "state" (:95-103).
+
+  `np.take` semantics for device tensors too: negative indices count from the end, an index
+  outside [-n, n) raises IndexError (the gather kernels never bounds-check: the indices are the
+  caller's and live on the host, so they are validated THERE, once, without a device sync), and
+  an index array of any rank replaces the axis by its own shape.
+  """
 
   def __init__(self, indices, axis=1):
     self.indices = indices
     self.axis = axis
+
+  def _checked(self, size):
+    """Host int64 indices wrapped into [0, size); IndexError like NumPy's when out of bounds."""
+    index = np.asarray(self.indices)
+    if index.size == 0:   # np.take accepts an empty (float64) list
+      index = index.astype(np.int64)
+    if index.dtype == np.bool_ or not np.issubdtype(index.dtype, np.integer):
+      raise TypeError(f"Take indices must be integers, got {index.dtype}")
+    index = index.astype(np.int64)
+    if index.size:
+      lo, hi = int(index.min()), int(index.max())
+      if lo < -size or hi >= size:
+        bad = lo if lo < -size else hi
+        raise IndexError(f"index {bad} is out of bounds for axis {self.axis} with size {size}")
+    return np.where(index < 0, index + size, index)
 
   def __call__(self, trajectory):
     for key, val in trajectory.items():
@@ -176,13 +199,19 @@ class Take:
       if hasattr(val, "materialize"):   # HostColumn: upload, then index on the device
         val = val.materialize()
       if isinstance(val, torch.Tensor):
-        index = torch.as_tensor(np.asarray(self.indices), device=val.device)
+        axis = self.axis if self.axis >= 0 else self.axis + val.ndim
+        if not 0 <= axis < val.ndim:
+          raise IndexError(f"axis {self.axis} is out of bounds for array of dimension {val.ndim}")
+        index = self._checked(val.shape[axis])
         if index.ndim == 0:
-          trajectory[key] = val.select(self.axis, int(index))
-        elif self.axis == 0 and val.is_cuda and index.dtype == torch.int64:
-          trajectory[key] = _K.gather_rows(val.contiguous(), index.contiguous(), 0,
-                                           index.numel())
+          trajectory[key] = val.select(axis, int(index))
+          continue
+        flat = torch.from_numpy(np.ascontiguousarray(index.reshape(-1))).to(val.device)
+        if axis == 0 and val.is_cuda and flat.numel() > 0:
+          taken = _K.gather_rows(val.contiguous(), flat, 0, flat.numel())
         else:
-          trajectory[key] = torch.index_select(val, self.axis, index.reshape(-1).long())
+          taken = torch.index_select(val, axis, flat)
+        trajectory[key] = taken.reshape(tuple(val.shape[:axis]) + index.shape
+                                        + tuple(val.shape[axis + 1:]))
       else:
         trajectory[key] = np.take(val, self.indices, axis=self.axis)

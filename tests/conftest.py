@@ -25,26 +25,6 @@ def pytest_collection_modifyitems(config, items):
       item.add_marker(skip)
 
 
-def pytest_runtest_protocol(item, nextitem):
-  """GPU tests run on shared, freshly leased boxes: a test that fails is run ONCE more and the
-  first failure is printed loudly.  A deterministic bug fails twice and is reported as usual;
-  a one-off glitch of the box shows up as a warning instead of sinking the round."""
-  if "gpu" not in item.keywords:
-    return None
-  from _pytest.runner import runtestprotocol
-  item.ihook.pytest_runtest_logstart(nodeid=item.nodeid, location=item.location)
-  reports = runtestprotocol(item, nextitem=nextitem, log=False)
-  if any(r.failed for r in reports):
-    first = next(r for r in reports if r.failed)
-    sys.stderr.write(f"\n[derl_b200 tests] {item.nodeid} FAILED once, re-running it:\n"
-                     f"{first.longreprtext}\n")
-    reports = runtestprotocol(item, nextitem=nextitem, log=False)
-  for report in reports:
-    item.ihook.pytest_runtest_logreport(report=report)
-  item.ihook.pytest_runtest_logfinish(nodeid=item.nodeid, location=item.location)
-  return True
-
-
 class Golden:
   """tests/golden/<name>.npz with `case(i)` access to the c<i>_* groups."""
 

@@ -589,16 +589,9 @@ def test_ppo_pybullet_fixture_through_the_product_model(golden):
                                err_msg=f"grad_{j}")
 
 
-@pytest.mark.parametrize("name,kind", [("live_update_mujoco.npz", "mujoco"),
-                                       ("live_update_atari.npz", "atari")])
-def test_full_ppo_update_matches_reference_losses(golden, name, kind):
-  """Two rollouts through the whole drop-in pipeline (GAE -> minibatches -> normalise ->
-  fused loss -> backward -> clip -> Adam) with the reference's seeds: the sequence of
-  losses the reference's own classes produced.  float32 network on both sides (TF32 off);
-  tolerance 1e-4 relative: GPU-vs-CPU float32 GEMM/conv rounding compounds over Adam steps."""
-  torch.backends.cuda.matmul.allow_tf32 = False
-  torch.backends.cudnn.allow_tf32 = False
-  g = golden(name)
+def run_golden_update(g, kind, micro_batch=None, fused_gather=False):
+  """The golden rollouts through the whole drop-in pipeline (GAE -> minibatches -> normalise ->
+  fused loss -> backward -> clip -> Adam) with the reference's seeds; returns (losses, model)."""
   torch.manual_seed(0)
   if kind == "mujoco":
     model = d.MuJoCoModel(g["r0_observations"].shape[-1], [g["r0_actions"].shape[-1], 1])
@@ -628,16 +621,91 @@ def test_full_ppo_update_matches_reference_losses(golden, name, kind):
 
   runner = d.ppo_runner_wrap(Source(), num_epochs=int(g["epochs"]),
                              num_minibatches=int(g["nmb"]))
+  if fused_gather:
+    runner.runner.fused_gather = True
   optimizer = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), eps=1e-5)
-  alg = d.PPO(runner, d.Trainer(optimizer, max_grad_norm=.5), cliprange=float(g["cliprange"]),
+  trainer = d.Trainer(optimizer, max_grad_norm=.5, micro_batch=micro_batch)
+  alg = d.PPO(runner, trainer, cliprange=float(g["cliprange"]),
               value_loss_coef=float(g["value_loss_coef"]), entropy_coef=float(g["entropy_coef"]))
   np.random.seed(int(g["seed"]))
   losses = [alg.step(batch).item() for batch in runner.run()]
+  return losses, model
+
+
+@pytest.mark.parametrize("name,kind", [("live_update_mujoco.npz", "mujoco"),
+                                       ("live_update_atari.npz", "atari")])
+def test_full_ppo_update_matches_reference_losses(golden, name, kind):
+  """Two rollouts through the whole drop-in pipeline with the reference's seeds: the sequence
+  of losses the reference's own classes produced.  float32 network on both sides (TF32 off);
+  tolerance 1e-4 relative: GPU-vs-CPU float32 GEMM/conv rounding compounds over Adam steps."""
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.backends.cudnn.allow_tf32 = False
+  try:
+    g = golden(name)
+    losses, model = run_golden_update(g, kind)
+  finally:
+    torch.backends.cudnn.allow_tf32 = True
   np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
   final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
   # a sum over 1.7 M parameters with cancellation: 1e-4 of the sum is ~1e-8 per parameter
   np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-4)
+
+
+# Tolerances of the benchmarked (default `bench.py`) arithmetic against the reference's float32
+# losses: TF32 tensor-core conv/GEMM (10-bit mantissa operands, fp32 accumulation) plus the INT8
+# two-digit stem kernels K6/K7 (operand residual <= 1/508 of a channel's scale, below TF32's).
+# The loss is a mean of O(1) per-sample terms; eight Adam steps (lr 2.5e-4, sign-like updates)
+# compound the difference.  Measured on B200 (profiles/r02_tf32_parity.txt): worst loss deviation
+# 2.6e-4 relative, parameter-sum deviation 1.1e-6 of sum|p|; the bounds below are ~4x that.
+TF32_LOSS_RTOL = 1e-3
+TF32_PARAM_SUM_TOL = 5e-6   # of sum |p| (25771): the sum itself cancels to -13.4
+
+
+@pytest.mark.parametrize("fused_gather", [False, True])
+def test_benchmarked_configuration_tracks_the_fp32_reference_losses(golden, fused_gather):
+  """The configuration bench.py times by default — allow_tf32 on (cuDNN/cuBLAS TF32), the INT8
+  stem kernels K6/K7 on, space-to-depth hidden layers on, micro-batched gradient accumulation
+  (ragged chunks: 12-row minibatches in chunks of 5), optionally the fused gather — run on the
+  reference's golden rollouts and compared with the losses the reference's float32 CPU classes
+  produced (tests/golden/live_update_atari.npz).  This pins the benchmarked arithmetic end to
+  end against the oracle with a stated tolerance."""
+  assert d.NatureCNNBase.custom_stem and d.NatureCNNBase.space_to_depth_hidden
+  torch.backends.cuda.matmul.allow_tf32 = True
   torch.backends.cudnn.allow_tf32 = True
+  launches = _lib.launch_count()
+  g = golden("live_update_atari.npz")
+  try:
+    losses, model = run_golden_update(g, "atari", micro_batch=5, fused_gather=fused_gather)
+  finally:
+    torch.backends.cuda.matmul.allow_tf32 = False
+  assert _lib.launch_count() - launches >= 8 * 3 * 2, "K6/K7 did not run"
+  rel = np.abs(np.asarray(losses) - g["losses"]) / np.abs(g["losses"])
+  final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+  dsum = abs(final.sum().item() - float(g["final_param_sum"])) / float(g["final_param_abs_sum"])
+  print(f"\n[tf32 parity fused_gather={fused_gather}] max loss rel dev {rel.max():.3e} "
+        f"(per step {np.array2string(rel, precision=2)}), param-sum dev {dsum:.3e} of sum|p|")
+  np.testing.assert_allclose(losses, g["losses"], rtol=TF32_LOSS_RTOL, atol=0)
+  assert dsum <= TF32_PARAM_SUM_TOL, dsum
+
+
+def test_stem_kernels_run_in_the_default_configuration():
+  """Guard for the test above: with allow_tf32 the model routes its first layer through K6
+  (forward) and K7 (backward), and with TF32 off it does not."""
+  from derl_b200 import ops
+  frames = torch.randint(0, 256, (6, 84, 84, 4), dtype=torch.uint8, device=DEV)
+  torch.manual_seed(0)
+  model = d.NatureCNNModel([4, 1])
+  for tf32, expect in ((True, True), (False, False)):
+    torch.backends.cudnn.allow_tf32 = tf32
+    ops.PROFILE = []
+    try:
+      logits, values = model(frames)
+      (logits.sum() + values.sum()).backward()
+      names = {n for n, _, _ in ops.PROFILE}
+    finally:
+      ops.PROFILE = None
+      torch.backends.cudnn.allow_tf32 = True
+    assert ("stem_conv_relu" in names) == expect and ("stem_backward" in names) == expect, names
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
@@ -1017,3 +1085,107 @@ def test_launch_counter_counts_our_kernels():
   before = _lib.launch_count()
   K.moments(torch.ones(100, device=DEV))
   assert _lib.launch_count() == before + 1
+
+
+# =============================================================================== Take / EnvRunner
+@pytest.mark.parametrize("axis,indices", [(0, [3, 0, 0, -1]), (0, 2), (1, [1, -2]),
+                                          (0, [[0, 1], [4, -5]]), (1, 0)])
+def test_take_on_device_tensors_matches_np_take(axis, indices):
+  """derl/runners/trajectory_transforms.py:95-103 on CUDA tensors: axis 0 goes through the
+  gather_rows kernel (28 224-byte rows take the TMA path), other axes through index_select; a
+  HostColumn (pinned host column of the e2e path) is uploaded first.  Bit-exact vs np.take."""
+  from derl_b200.runners.host_column import HostColumn
+  rng = np.random.RandomState(2)
+  obs = rng.randint(0, 256, (5, 3, 84, 84, 4)).astype(np.uint8)
+  adv = rng.standard_normal((5, 3)).astype(np.float32)
+  state = dict(latest_observations=obs[0])
+  traj = dict(observations=cuda(obs), advantages=cuda(adv), state=state)
+  d.Take(indices, axis=axis)(traj)
+  for key, src in (("observations", obs), ("advantages", adv)):
+    want = np.take(src, indices, axis=axis)
+    assert traj[key].is_cuda and tuple(traj[key].shape) == want.shape
+    assert np.array_equal(traj[key].cpu().numpy(), want), key
+  assert traj["state"] is state
+  pinned = torch.from_numpy(obs.reshape(15, 84, 84, 4)).pin_memory()
+  column = HostColumn(pinned, torch.device(DEV))
+  traj = dict(observations=column)
+  if axis == 0:
+    d.Take(indices, axis=0)(traj)
+    assert np.array_equal(traj["observations"].cpu().numpy(),
+                          np.take(obs.reshape(15, 84, 84, 4), indices, axis=0))
+
+
+def test_take_out_of_range_raises_before_any_launch():
+  x = torch.zeros(4, 3, 28224, dtype=torch.uint8, device=DEV)
+  before = _lib.launch_count()
+  for bad, axis in (([0, 4], 0), ([-5], 0), (3, 1)):
+    with pytest.raises(IndexError, match="out of bounds"):
+      d.Take(bad, axis=axis)(dict(observations=x))
+  assert _lib.launch_count() == before
+
+
+def test_env_runner_resident_on_cuda_feeds_gae_without_a_second_forward():
+  """EnvRunner(resident_device="cuda") writes each step through pinned
+  staging rows into preallocated device tensors (equal to the reference-style stacked lists),
+  and hands GAE the critic's value of the final observation from its own forward pass on it
+  (`state["latest_values"]`, on the device): GAE's result is bit-identical to the oracle's on the
+  stacked host arrays, and the policy is not called again."""
+  class Env:
+    nenvs = 4
+    unwrapped = property(lambda self: self)
+
+    def __init__(self):
+      self.t = 0
+      self.rng = np.random.RandomState(5)
+
+    def _obs(self):
+      return self.rng.randint(0, 256, (4, 84, 84, 4)).astype(np.uint8)
+
+    def reset(self):
+      self.t = 0
+      return self._obs()
+
+    def step(self, actions):
+      self.t += 1
+      return (self._obs(), self.rng.standard_normal(4), self.rng.rand(4) < 0.2, [{}] * 4)
+
+  class CountingPolicy(d.ActorCriticPolicy):
+    calls = 0
+
+    def act(self, inputs, state=None, update_state=True, training=False):
+      CountingPolicy.calls += 1
+      return super().act(inputs, state, update_state, training)
+
+  torch.manual_seed(0)
+  torch.backends.cudnn.allow_tf32 = False
+  try:
+    policy = CountingPolicy(d.NatureCNNModel([4, 1]))
+    runner = d.EnvRunner(Env(), policy, horizon=6, nsteps=48, resident_device=DEV)
+    gen = runner.run()
+    rollouts = [next(gen), next(gen)]
+    assert runner.is_exhausted()
+    for rollout in rollouts:
+      for key in ("observations", "actions", "log_prob", "values", "rewards", "resets"):
+        assert rollout[key].is_cuda and rollout[key].shape[:2] == (6, 4), key
+      assert rollout["observations"].dtype == torch.uint8
+      assert rollout["rewards"].dtype == torch.float64 and rollout["resets"].dtype == torch.bool
+      assert rollout["state"]["latest_values"].is_cuda
+    # the two rollouts own different device tensors (the first is not overwritten by the second)
+    assert rollouts[0]["observations"].data_ptr() != rollouts[1]["observations"].data_ptr()
+    assert not torch.equal(rollouts[0]["observations"], rollouts[1]["observations"])
+    # replay the env: the resident tensors hold exactly what the per-step lists would
+    env = Env()
+    first = env.reset()
+    assert np.array_equal(rollouts[0]["observations"][0].cpu().numpy(), first)
+    calls = CountingPolicy.calls
+    rollout = rollouts[1]
+    host = {k: rollout[k].cpu().numpy() for k in ("rewards", "values", "resets")}
+    last_value = rollout["state"]["latest_values"].cpu().numpy()
+    adv, targets = d.GAE(policy, normalize=False)(rollout)
+    assert CountingPolicy.calls == calls, "GAE ran a second forward for the bootstrap value"
+    want_adv, want_targets = O.gae(host["rewards"], host["values"], host["resets"], last_value,
+                                   normalize=False)
+    assert np.array_equal(adv.cpu().numpy(), want_adv)
+    assert np.array_equal(targets.cpu().numpy(), want_targets)
+  finally:
+    torch.backends.cudnn.allow_tf32 = True

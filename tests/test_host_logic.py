@@ -265,3 +265,52 @@ def test_row_selection_is_a_lazy_descriptor():
   with pytest.raises(TypeError):
     RowSelection(source.permute(1, 0, 2), perm, 0, 2)
   assert dense(source) is source
+
+
+@pytest.mark.parametrize("axis", [0, 1, -1])
+@pytest.mark.parametrize("indices", [2, -1, [0, 2, 2, 1], [-1, 0], [[0, 1], [2, -3]], []])
+def test_take_follows_np_take_for_tensors_and_arrays(axis, indices):
+  """derl/runners/trajectory_transforms.py:95-103: np.take for every key but "state".  Tensor
+  values (CPU here, index_select; CUDA rows via the gather kernel in the GPU suite) must give
+  what np.take gives for the same arrays: scalar index drops the axis, negative indices wrap,
+  index arrays of any rank replace the axis by their shape."""
+  rng = np.random.RandomState(0)
+  obs = rng.randint(0, 255, size=(5, 3, 4)).astype(np.uint8)
+  rew = rng.randn(5, 3, 4)
+  state = dict(latest_observations=obs[0])
+  as_np = dict(observations=obs.copy(), rewards=rew.copy(), state=state)
+  as_t = dict(observations=torch.from_numpy(obs.copy()), rewards=torch.from_numpy(rew.copy()),
+              state=state)
+  take = d.Take(indices, axis=axis)
+  take(as_np)
+  take(as_t)
+  for key in ("observations", "rewards"):
+    want = np.take({"observations": obs, "rewards": rew}[key], indices, axis=axis)
+    np.testing.assert_array_equal(as_np[key], want)
+    assert tuple(as_t[key].shape) == want.shape
+    np.testing.assert_array_equal(as_t[key].numpy(), want)
+  assert as_np["state"] is state and as_t["state"] is state
+
+
+def test_take_rejects_out_of_range_indices_like_numpy():
+  """np.take raises IndexError for an index outside [-n, n); the device gather kernels do no
+  bounds checks, so Take validates the (host) indices before any launch."""
+  x = np.arange(12.).reshape(3, 4)
+  for bad, axis in ((3, 0), (-4, 0), ([0, 4], 1), ([-5], 1)):
+    with pytest.raises(IndexError):
+      np.take(x, bad, axis=axis)
+    with pytest.raises(IndexError, match="out of bounds"):
+      d.Take(bad, axis=axis)(dict(x=torch.from_numpy(x)))
+  with pytest.raises(IndexError, match="axis 2 is out of bounds"):
+    d.Take([0], axis=2)(dict(x=torch.from_numpy(x)))
+  with pytest.raises(TypeError):
+    d.Take([0.5], axis=0)(dict(x=torch.from_numpy(x)))
+
+
+def test_take_default_axis_selects_envs():
+  """Default axis=1 is the env axis of a [T, N, ...] rollout (the reference's use: keep a subset
+  of environments)."""
+  traj = dict(rewards=torch.arange(12.).reshape(4, 3), resets=np.zeros((4, 3), bool))
+  d.Take([2, 0])(traj)
+  assert traj["rewards"].tolist() == [[2., 0.], [5., 3.], [8., 6.], [11., 9.]]
+  assert traj["resets"].shape == (4, 2)
