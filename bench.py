@@ -64,7 +64,12 @@ def parse_args():
   p.add_argument("--no-alt", action="store_true",
                  help="skip the informational bf16-autocast-network measurement")
   p.add_argument("--no-cpu-baseline", action="store_true")
-  p.add_argument("--gae-sweep", action="store_true", help="also time the GAE kernel sweep")
+  p.add_argument("--no-gae-sweep", action="store_true",
+                 help="skip the GAE kernel sweep (BASELINE configs[4]; runs by default at N=1)")
+  p.add_argument("--no-small-configs", action="store_true",
+                 help="skip BASELINE configs[0] / configs[1] (Atari 8x128, MuJoCo 1x2048)")
+  p.add_argument("--alt-steps", type=int, default=5,
+                 help="timed steps of each informational alt_* measurement (capped by --steps)")
   return p.parse_args()
 
 
@@ -145,52 +150,178 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_update_throughput(args, nenvs, steps, warmup):
-  """The reference's CPU path (oracle port: NumPy GAE/shuffle/slice/normalise + CPU torch
-  NatureCNN/PPOLoss/Adam) on a bounded sample of the workload; returns samples/s."""
-  from oracle import derl_oracle as O
-  import derl_b200 as d
-  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
-  torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+def host_rollout(kind, horizon, nenvs, seed=0, nactions=4, obs_dim=17, act_dim=6):
+  """Seeded synthetic rollout as NumPy arrays with the dtypes EnvRunner + np.asarray produce
+  (SURVEY.md §8a a1, §8d).  Same generator calls as derl_b200.make_rollout(device="cpu"),
+  restated here so that the reference arm never imports derl_b200 (nor loads its .so)."""
+  import math
+  gen = torch.Generator()
+  gen.manual_seed(seed)
+  lead = (horizon,) if nenvs is None else (horizon, nenvs)
+  tail = () if nenvs is None else (nenvs,)
+  randn = lambda shape, dtype=torch.float32: torch.randn(shape, generator=gen, dtype=dtype)
+  rand = lambda shape: torch.rand(shape, generator=gen)
+  if kind == "atari":
+    obs = torch.randint(0, 256, lead + (84, 84, 4), generator=gen, dtype=torch.uint8)
+    latest = torch.randint(0, 256, tail + (84, 84, 4), generator=gen, dtype=torch.uint8)
+    actions = torch.randint(0, nactions, lead, generator=gen, dtype=torch.int64)
+    log_prob = -math.log(nactions) + 0.01 * randn(lead)
+    rewards = (torch.sign(randn(lead)) * (rand(lead) < 0.1)).to(torch.float64)
+    resets = rand(lead) < 0.01
+  else:
+    obs = randn(lead + (obs_dim,), torch.float64)
+    latest = randn(tail + (obs_dim,), torch.float64)
+    actions = randn(lead + (act_dim,))
+    log_prob = (-0.5 * actions ** 2 - 0.5 * math.log(2 * math.pi)).sum(-1) + 0.01 * randn(lead)
+    rewards = randn(lead, torch.float64)
+    resets = rand(lead) < 0.001
+  values = randn(lead + (1,))
+  out = dict(observations=obs, actions=actions, log_prob=log_prob, values=values,
+             rewards=rewards, resets=resets)
+  out = {k: v.numpy() for k, v in out.items()}
+  out["state"] = dict(latest_observations=latest.numpy())
+  return out
+
+
+def find_reference():
+  """The live reference tree, looked up as SURVEY.md §8c says: $DERL_REF -> baseline/_ref ->
+  /root/reference (none of them exists on the GPU box: the reference is pure Python, `pip
+  install` of it drops its sub-packages — setup.py lists packages=["derl"] only — so there is
+  no baseline/_ref to ship).  Returns the imported package or None."""
+  for cand in (os.environ.get("DERL_REF"), os.path.join(REPO, "baseline", "_ref"),
+               "/root/reference"):
+    if cand and os.path.isfile(os.path.join(cand, "derl", "runners", "onpolicy.py")):
+      for path in (os.path.join(REPO, "tests", "_stubs"), cand):   # gym / atari_py import stubs
+        if path not in sys.path:
+          sys.path.insert(0, path)
+      try:
+        import derl
+        import derl.summary
+        derl.summary.stop_recording()
+        return derl
+      except Exception as exc:   # noqa: BLE001 — any import problem means "not available here"
+        sys.stderr.write(f"[bench] reference at {cand} not importable: {exc!r}\n")
+  return None
+
+
+CPU_CONFIGS = {
+    "atari": dict(hp=dict(cliprange=HP["cliprange"], value_loss_coef=HP["value_loss_coef"],
+                          entropy_coef=HP["entropy_coef"]), lr=HP["lr"]),
+    # derl/factory/ppo.py:37-49 (MuJoCo defaults)
+    "mujoco": dict(hp=dict(cliprange=0.2, value_loss_coef=0.25, entropy_coef=0.0), lr=3e-4),
+}
+
+
+class HostArrayRunner:
+  """EnvRunner-shaped source yielding the same host rollout forever (for the live reference)."""
+
+  def __init__(self, rollout, policy, nenvs, horizon):
+    self.rollout, self.policy, self.horizon, self.nenvs = rollout, policy, horizon, nenvs
+    self.env = type("E", (), {"nenvs": nenvs, "unwrapped": property(lambda s: s)})()
+    self.nsteps, self.step_count = 10 ** 12, 0
+
+  def is_exhausted(self):
+    return False
+
+  def run(self, obs=None):
+    while True:
+      self.step_count += self.horizon * (self.nenvs or 1)
+      yield {k: (dict(v) if k == "state" else np.array(v)) for k, v in self.rollout.items()}
+
+
+def cpu_update_seconds(kind, nenvs, horizon, epochs, minibatches, steps, warmup, nactions=4,
+                       prefer_live=True):
+  """Seconds per PPO update of the reference's CPU path on a host rollout of the given shape,
+  with all the host threads this process may use.  The reference's own classes when its tree is
+  present (kind "live": TransformInteractions[GAE, MergeTimeBatch] -> IterateWithMinibatches ->
+  NormalizeAdvantages -> PPOLoss -> Trainer(Adam eps 1e-5, clip .5), derl/runners/onpolicy.py:
+  65-75, derl/alg/common.py:66-78), else the oracle port of the same steps (kind "port").
+  Returns (mean seconds per update, kind)."""
+  torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))  # torchrun exports OMP_NUM_THREADS=1
+  cfg = CPU_CONFIGS[kind]
+  rollout = host_rollout(kind, horizon, nenvs, seed=0, nactions=nactions)
+  ref = find_reference() if prefer_live else None
   torch.manual_seed(0)
-  model = O.NatureCNN(args.nactions)
-  optimizer = torch.optim.Adam(model.parameters(), lr=HP["lr"], eps=HP["eps"])
-  rollout = d.make_rollout("atari", args.horizon, nenvs, device="cpu", seed=0,
-                           nactions=args.nactions)
-  latest = torch.from_numpy(rollout["state"]["latest_observations"])
-  columns = {k: v for k, v in rollout.items() if k != "state"}
   np.random.seed(0)
   times = []
-  for it in range(warmup + steps):
+  if ref is not None:
+    model = ref.NatureCNNModel([nactions, 1]) if kind == "atari" else ref.MuJoCoModel(17, [6, 1])
+    model.to("cpu")
+    policy = ref.ActorCriticPolicy(model)
+    runner = ref.ppo_runner_wrap(HostArrayRunner(rollout, policy, nenvs, horizon),
+                                 num_epochs=epochs, num_minibatches=minibatches)
+    optimizer = torch.optim.Adam(model.parameters(), lr=cfg["lr"], eps=HP["eps"])
+    alg = ref.PPO(runner, ref.Trainer(optimizer, max_grad_norm=HP["max_grad_norm"]), **cfg["hp"])
+    it = runner.run()
+    for i in range(warmup + steps):
+      t0 = time.perf_counter()
+      for _ in range(epochs * minibatches):
+        alg.step(next(it))
+      if i >= warmup:
+        times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), "live"
+  from oracle import derl_oracle as O
+  model = O.NatureCNN(nactions) if kind == "atari" else O.MuJoCoMLP(17, 6)
+  optimizer = torch.optim.Adam(model.parameters(), lr=cfg["lr"], eps=HP["eps"])
+  latest = torch.from_numpy(rollout["state"]["latest_observations"])
+  columns = {k: v for k, v in rollout.items() if k != "state"}
+  for i in range(warmup + steps):
     t0 = time.perf_counter()
     with torch.no_grad():
-      last_value = model(latest)[-1].numpy()
-    O.ppo_update(model, optimizer, columns, last_value, gamma=HP["gamma"],
-                 lambda_=HP["lambda_"], num_epochs=args.epochs,
-                 num_minibatches=args.minibatches, cliprange=HP["cliprange"],
-                 value_loss_coef=HP["value_loss_coef"], entropy_coef=HP["entropy_coef"],
-                 max_grad_norm=HP["max_grad_norm"])
-    if it >= warmup:
+      last_value = model(latest if nenvs is not None else latest[None])[-1].numpy()
+    if nenvs is None:
+      last_value = last_value[0]
+    O.ppo_update(model, optimizer, columns, last_value, gamma=HP["gamma"], lambda_=HP["lambda_"],
+                 num_epochs=epochs, num_minibatches=minibatches,
+                 max_grad_norm=HP["max_grad_norm"], batched=nenvs is not None, **cfg["hp"])
+    if i >= warmup:
       times.append(time.perf_counter() - t0)
-  samples = args.horizon * nenvs * args.epochs
-  return samples * len(times) / sum(times), sum(times) / len(times)
+  return sum(times) / len(times), "port"
+
+
+def cpu_update_throughput(args, nenvs, steps, warmup):
+  sec, kind = cpu_update_seconds("atari", nenvs, args.horizon, args.epochs, args.minibatches,
+                                 steps, warmup, args.nactions)
+  return args.horizon * nenvs * args.epochs / sec, sec, kind
+
+
+# cpu_baseline.kind in the bench contract: "reference" = the reference's own code, "port" = oracle
+CPU_KIND = {"live": "reference", "port": "port"}
+
+
+def cpu_sample_text(args, sec, kind):
+  what = {"live": "the reference's own classes (derl.ppo_runner_wrap + PPO/Trainer) on CPU",
+          "port": "oracle port of the reference path (oracle/derl_oracle.py) on CPU"}[kind]
+  return (f"{args.cpu_envs} envs x {args.horizon} steps (a 1/{args.envs_per_gpu // args.cpu_envs} "
+          f"env-axis sample of the {args.envs_per_gpu}-env workload: per-sample cost of the CPU "
+          f"path does not depend on the env count), {args.epochs} epochs x {args.minibatches} "
+          f"minibatches, NatureCNN float32, full update, {sec:.2f} s per step; {what}")
 
 
 def run_reference(args, rank):
+  """The reference's CPU implementation of the path, on a bounded sample, rank 0 only.  Never
+  imports derl_b200 (no CUDA library is loaded in this arm)."""
   if rank != 0:
     return
-  value, sec = cpu_update_throughput(args, args.cpu_envs, args.steps, min(args.warmup, 1))
+  value, sec, kind = cpu_update_throughput(args, args.cpu_envs, args.steps, args.warmup)
   cores = torch.get_num_threads()
-  sample = (f"{args.cpu_envs} envs x {args.horizon} steps (of {args.envs_per_gpu} per GPU), "
-            f"{args.epochs} epochs x {args.minibatches} minibatches, NatureCNN fp32, full update")
+  config = workload_config(args, args.gpus)
+  config.update({
+      "workload": (f"atari-shaped PPO update on the HOST CPU, bounded sample: {args.cpu_envs} envs "
+                   f"x {args.horizon} steps of the {args.envs_per_gpu}-envs/GPU workload, 84x84x4 "
+                   f"u8 obs, {args.epochs} epochs x {args.minibatches} minibatches, NatureCNN "
+                   f"A={args.nactions}, float32 (BASELINE configs[2] shape per sample)"),
+      "envs_total": args.cpu_envs, "micro_batch": None, "network": "fp32 (CPU)",
+      "l2": "n/a (CPU)", "parallelism": f"{cores} host threads"})
   line = {
       "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value,
-      "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+      "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32 (GAE f64 registers)", "data": "synthetic",
-      "config": workload_config(args, args.gpus),
-      "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                       "sample": sample},
+      "config": config,
+      "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores,
+                       "kind": CPU_KIND[kind], "source": kind,
+                       "sample": cpu_sample_text(args, sec, kind)},
       "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
   }
@@ -355,6 +486,79 @@ def gae_sweep(d, hbm_peak):
   return rows
 
 
+# BASELINE configs[0] / configs[1]: the reference's own default shapes, through the public API
+SMALL_CONFIGS = {
+    "C1_atari_8x128": dict(kind="atari", nenvs=8, horizon=128, epochs=4, minibatches=4),
+    "C2_mujoco_1x2048": dict(kind="mujoco", nenvs=None, horizon=2048, epochs=10, minibatches=32),
+}
+
+
+def small_config_gpu(d, cfg, mode, updates, warmup):
+  """ms per PPO update of one small config.  mode: "eager" = ppo_runner_wrap + PPO + Trainer
+  stepped minibatch by minibatch; "graphed" = the same with GraphedTrainer (CUDA-graph replay);
+  "learn" = what a drop-in user runs, `PPO.learn()` with the defaults (which picks the fused
+  whole-update kernel when the model qualifies)."""
+  kind = cfg["kind"]
+  hp, lr = CPU_CONFIGS[kind]["hp"], CPU_CONFIGS[kind]["lr"]
+  torch.manual_seed(0)
+  model = d.NatureCNNModel([4, 1]) if kind == "atari" else d.MuJoCoModel(17, [6, 1])
+  policy = d.ActorCriticPolicy(model)
+  per_update = cfg["epochs"] * cfg["minibatches"]
+  rollout_steps = cfg["horizon"] * (cfg["nenvs"] or 1)
+  source = d.SyntheticRolloutRunner(policy, kind, cfg["nenvs"], cfg["horizon"],
+                                    nsteps=None, device="cuda", seed=1)
+  runner = d.ppo_runner_wrap(source, num_epochs=cfg["epochs"], num_minibatches=cfg["minibatches"])
+  if mode == "graphed":
+    anneal = d.LinearAnneal(lr, 1e9, device="cuda", name="lr")
+    opt = torch.optim.Adam(model.parameters(), lr=anneal.get_tensor(), eps=HP["eps"],
+                           capturable=True)
+    trainer = d.GraphedTrainer(opt, anneals=[anneal], max_grad_norm=HP["max_grad_norm"])
+  else:
+    opt = torch.optim.Adam(model.parameters(), lr=lr, eps=HP["eps"], fused=mode == "eager")
+    trainer = d.Trainer(opt, max_grad_norm=HP["max_grad_norm"])
+  alg = d.PPO(runner, trainer, **hp)
+  np.random.seed(0)
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  if mode == "learn":
+    def run(n):
+      source.nsteps = source.step_count + n * rollout_steps
+      alg.learn(progress=False)
+    run(warmup)
+    torch.cuda.synchronize()
+    start.record()
+    run(updates)
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / updates, None
+  it = runner.run()
+  for _ in range(warmup * per_update):
+    alg.step(next(it))
+  torch.cuda.synchronize()
+  start.record()
+  for _ in range(updates * per_update):
+    loss = alg.step(next(it))
+  stop.record()
+  torch.cuda.synchronize()
+  return start.elapsed_time(stop) / updates, float(loss)
+
+
+def small_configs(d):
+  out = {}
+  for name, cfg in SMALL_CONFIGS.items():
+    samples = cfg["horizon"] * (cfg["nenvs"] or 1) * cfg["epochs"]
+    entry = {"optimizer_steps_per_update": cfg["epochs"] * cfg["minibatches"],
+             "samples_per_update": samples, "unit": "samples/s"}
+    for mode in ("eager", "graphed", "learn"):
+      ms, loss = small_config_gpu(d, cfg, mode, updates=5, warmup=3)
+      entry[mode] = {"ms_per_update": ms, "value": samples / ms * 1e3}
+    sec, kind = cpu_update_seconds(cfg["kind"], cfg["nenvs"], cfg["horizon"], cfg["epochs"],
+                                   cfg["minibatches"], steps=2, warmup=1)
+    entry["cpu"] = {"ms_per_update": sec * 1e3, "value": samples / sec, "kind": CPU_KIND[kind],
+                    "source": kind, "cores": torch.get_num_threads()}
+    out[name] = entry
+  return out
+
+
 def run_ours(args, rank, world, local):
   import derl_b200 as d
   from derl_b200 import _lib, ops
@@ -439,15 +643,32 @@ def run_ours(args, rank, world, local):
       f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45,
                                         max_name_column_width=90))
 
+  alt_steps = max(1, min(args.steps, args.alt_steps))
+  # ---- the same update at the REFERENCE's arithmetic: float32 cuDNN/cuBLAS (TF32 off, which
+  # also routes the stem through K4 + cuDNN instead of the INT8 kernels K6/K7).  The
+  # precision-matched companion of `value` (derl/models.py:102-124 is float32 end to end).
+  alt_fp32 = None
+  if args.net != "fp32" and not args.no_alt:
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sec_p, losses_p = timed_updates(alg, runner, nbatches, alt_steps, 2, world, False)
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    alt_fp32 = {"network": "fp32 (allow_tf32 off: cuDNN/cuBLAS float32, no INT8 stem kernels)",
+                "dtype": "f32; GAE f64 registers; u8 gather",
+                "value": samples_per_step * alt_steps / sec_p, "unit": "samples/s",
+                "ms_per_step": sec_p / alt_steps * 1e3, "steps": alt_steps, "warmup": 2,
+                "last_loss": float(losses_p[-1])}
+
   # ---- informational: the same update with the network under bf16 autocast
   alt = None
   if args.net != "bf16" and not args.no_alt:
     model.autocast_dtype = torch.bfloat16
-    sec_a, _ = timed_updates(alg, runner, nbatches, max(1, args.steps - 1), 2, world, False)
+    sec_a, _ = timed_updates(alg, runner, nbatches, alt_steps, 2, world, False)
     model.autocast_dtype = None
     alt = {"network": "bf16 autocast (parameters fp32)",
-           "value": samples_per_step * max(1, args.steps - 1) / sec_a, "unit": "samples/s",
-           "ms_per_step": sec_a / max(1, args.steps - 1) * 1e3}
+           "value": samples_per_step * alt_steps / sec_a, "unit": "samples/s",
+           "ms_per_step": sec_a / alt_steps * 1e3, "steps": alt_steps}
 
   # ---- informational: minibatch gather fused into the stem kernels: the
   # observations of a minibatch are never materialised, K6/K7 read the rollout rows in place.
@@ -456,11 +677,11 @@ def run_ours(args, rank, world, local):
   fused = None
   if not args.no_alt:
     runner.runner.fused_gather = True
-    sec_f, _ = timed_updates(alg, runner, nbatches, max(1, args.steps - 1), 2, world, False)
+    sec_f, _ = timed_updates(alg, runner, nbatches, alt_steps, 2, world, False)
     runner.runner.fused_gather = False
     fused = {"what": "IterateWithMinibatches(fused_gather=True): stem kernels gather rows in place",
-             "value": samples_per_step * max(1, args.steps - 1) / sec_f, "unit": "samples/s",
-             "ms_per_step": sec_f / max(1, args.steps - 1) * 1e3}
+             "value": samples_per_step * alt_steps / sec_f, "unit": "samples/s",
+             "ms_per_step": sec_f / alt_steps * 1e3, "steps": alt_steps}
 
   # ---- e2e: rollout in pinned host memory, uploaded inside the timed region
   e2e = None
@@ -482,15 +703,20 @@ def run_ours(args, rank, world, local):
            "ms_per_step": sec_h / args.steps * 1e3}
     del host_source, alg_h, runner_h
 
-  sweep = gae_sweep(d, hbm_peak) if (args.gae_sweep and rank == 0) else None
+  # free the big rollouts before the side measurements
+  del alg, runner
+  source._cached = None
+  torch.cuda.empty_cache()
+  # BASELINE configs[4] (the "GAE HBM GB/s (frac of peak)" half of the metric) and configs[0..1]
+  sweep = gae_sweep(d, hbm_peak) if (rank == 0 and world == 1 and not args.no_gae_sweep) else None
+  small = small_configs(d) if (rank == 0 and world == 1 and not args.no_small_configs) else None
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    v, s = cpu_update_throughput(args, args.cpu_envs, 1, 1)
-    cpu = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-           "sample": (f"{args.cpu_envs} envs x {horizon} steps, {args.epochs} epochs x "
-                      f"{args.minibatches} minibatches, NatureCNN fp32 full update, "
-                      f"{s:.1f} s per step, 1 warm-up + 1 timed")}
+    v, sec_c, kind = cpu_update_throughput(args, args.cpu_envs, 1, 1)
+    cpu = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(),
+           "kind": CPU_KIND[kind], "source": kind,
+           "sample": cpu_sample_text(args, sec_c, kind) + ", 1 warm-up + 1 timed"}
 
   if rank == 0:
     line = {
@@ -503,12 +729,14 @@ def run_ours(args, rank, world, local):
                   "bf16": "f32 params, bf16 autocast network; GAE f64 registers; u8 gather"}[args.net],
         "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_network": alt,
-        "alt_fused_gather": fused,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_fp32": alt_fp32,
+        "alt_network": alt, "alt_fused_gather": fused,
         "last_loss": last_loss,
     }
     if sweep is not None:
       line["gae_sweep"] = sweep
+    if small is not None:
+      line["small_configs"] = small
     print(json.dumps(line), flush=True)
 
 

@@ -139,9 +139,11 @@ class Alg:
   def step(self, data):
     return self.trainer.step(self, data)
 
-  def learn(self):
+  def learn(self, progress=True):
+    """Performs learning until the runner is exhausted (reference :100-106).  `progress=False`
+    (extension) drops the tqdm bar."""
     from tqdm import tqdm
-    with tqdm(total=len(self.runner)) as pbar:
+    with tqdm(total=len(self.runner), disable=not progress) as pbar:
       for data in self.runner.run():
         pbar.update(self.runner.step_count - pbar.n)
         self.step(data)
