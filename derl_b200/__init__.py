@@ -1,7 +1,7 @@
 """derl_b200 — B200-native (sm_100a) PPO rollout-processing / update data path behind
 mknbv/derl's Python API: GAE -> minibatch gather -> fused PPO loss, rollout resident in HBM.
 
-Importing this package loads libderl_b200.so (build it with `python -m derl_b200.build`);
+Importing this package loads libderl_b200.so (build it with `python __graft_entry__.py`);
 there is no CPU fallback — without the library the import fails, without an sm_100 GPU
 every op raises.
 """

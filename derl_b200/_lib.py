@@ -8,7 +8,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libderl_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 GAE_AUTO, GAE_DIRECT, GAE_TMA = 0, 1, 2
 GAE_STATS = 3
@@ -55,6 +55,11 @@ SIGNATURES = {
     "derl_b200_stem_backward_workspace_bytes": (_size, []),
     "derl_b200_stem_backward": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _size,
                                       _ptr]),
+    "derl_b200_ppo_mlp_update_smem_bytes": (_size, [_int, _int]),
+    "derl_b200_ppo_mlp_update": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _int, _ptr, _ptr, _ptr,
+                                        _ptr, _ptr, _i64, _ptr, _i64, _i64, _int, _f64, _int, _f64,
+                                        _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _ptr, _ptr,
+                                        _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,
                                   _f64, _ptr, _ptr, _ptr]),
 }
@@ -70,7 +75,7 @@ def load():
   if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build the CUDA library first "
-        "(`python -m derl_b200.build` or `__graft_entry__.build()`); derl_b200 has no "
+        "(`python __graft_entry__.py`, i.e. `__graft_entry__.build()`); derl_b200 has no "
         "CPU or PyTorch fallback")
   lib = ctypes.CDLL(LIB_PATH)
   for name, (restype, argtypes) in SIGNATURES.items():
@@ -78,7 +83,7 @@ def load():
     fn.restype, fn.argtypes = restype, argtypes
   if lib.derl_b200_abi_version() != ABI_VERSION:
     raise ImportError(f"libderl_b200.so ABI {lib.derl_b200_abi_version()} != {ABI_VERSION}; "
-                      "rebuild with `python -m derl_b200.build --force`")
+                      "rebuild with `python __graft_entry__.py`")
   _lib = lib
   return lib
 

@@ -156,3 +156,26 @@ class PPO(Alg):
     loss_fn = PPOLoss(runner.policy, cliprange=cliprange, value_loss_coef=value_loss_coef,
                       entropy_coef=entropy_coef, name=name)
     super().__init__(runner, trainer, loss_fn, name=name)
+
+  fused_update = True   # class-wide switch: let learn() use the whole-update kernel (K8)
+  last_losses = None
+
+  def learn(self, progress=True):
+    """Reference semantics (derl/alg/common.py:100-106: step on every minibatch until the
+    runner is exhausted).  When the pipeline is the stock one on a fusable model
+    (alg/fused_mlp.py) each rollout's epochs x minibatches run as one launch of the persistent
+    update kernel instead of ~150 launches per minibatch."""
+    from .fused_mlp import FusedMLPUpdate
+    plan = FusedMLPUpdate.plan(self) if self.fused_update else None
+    if plan is None:
+      return super().learn(progress=progress)
+    from tqdm import tqdm
+    with tqdm(total=len(self.runner), disable=not progress) as pbar:
+      for rollout in plan.inner.run():
+        pbar.update(self.runner.step_count - pbar.n)
+        self.last_losses = plan.run(rollout)   # [nsteps] device tensor of this update's losses
+        if self.last_losses is None:           # e.g. summaries being recorded: ordinary path
+          for data in plan.iterate.minibatches(rollout):
+            if plan.normalize is not None:
+              plan.normalize(data)
+            self.step(data)

@@ -1,0 +1,559 @@
+// K8 — one launch = one whole PPO update of the MuJoCo-shaped actor-critic (two tanh MLPs
+// obs -> 64 -> 64 -> {D, 1} with a state-independent log-std): every epoch, every minibatch,
+//   permutation gather -> advantage normalisation -> both forward passes -> fused PPO loss
+//   (diagonal Gaussian, forward + backward) -> both backward passes -> clip_grad_norm_ -> Adam.
+//
+// Replaces, for BASELINE configs[1] (1 env x 2048 steps, 10 epochs x 32 minibatches of 64), the
+// reference's 320 trips per update around IterateWithMinibatches.run (derl/runners/onpolicy.py:
+// 51-62), NormalizeAdvantages (trajectory_transforms.py:89-92), MuJoCoModel.forward
+// (derl/models.py:261-271), PPOLoss (derl/alg/ppo.py:100-108), Trainer.step (derl/alg/common.py:
+// 66-78: backward, clip_grad_norm_, optimizer.step) — ~150 ATen launches each.  At a minibatch
+// of 64 rows and 11 k parameters none of that is bandwidth or FLOP work: the eager path spends
+// 1.6 ms per optimiser step on launches and Python, a CUDA-graph replay 0.25 ms.  Here the
+// whole update is one persistent CTA: parameters and their gradients live in shared memory for
+// all 320 steps (odd row pitches make every GEMM operand access conflict-free), a step is
+// ~30 k cycles of fp32 FMA work, and Adam's moment vectors are the only per-step global traffic
+// (88 KB, L2-resident).  fp32 FMA on CUDA cores, not tensor cores: the contract is the
+// reference's float32 (rtol 1e-5 on the loss), and [64 x 64 x 64] GEMMs on one SM are
+// latency-, not throughput-bound.
+//
+// Thread roles: 512 threads; threads 0-255 work on the policy network, 256-511 on the value
+// network.  A [64 x 64] GEMM is 256 threads x (4 x 4) register tile, rows tm + 16 i, columns
+// tn + 16 j (tm = t / 16, tn = t % 16), so that a warp reads 2 distinct A and 16 consecutive B
+// addresses per step of the reduction.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ppo_terms.cuh"
+
+namespace derl {
+namespace {
+
+constexpr int kH = 64;          // hidden width of both MLPs
+constexpr int kHP = kH + 1;     // odd pitch of a [*, 64] array in shared memory
+constexpr int kRows = 64;       // rows per pass (a larger minibatch accumulates over passes)
+constexpr int kThreads = 512;
+constexpr int kNet = 256;       // threads per network
+constexpr int kTensors = 13;    // W1 b1 W2 b2 W3 b3 (policy), the same (value), logstd
+constexpr int kMaxAct = 32;
+
+struct MlpTensor {
+  float* w;
+  float* m;
+  float* v;
+  int rows, cols, off, pitch;   // off / pitch: position inside the shared parameter block
+};
+
+// Shared-memory plan, identical on host and device (float offsets unless noted).
+struct Carve {
+  int OP, DP;                   // odd pitches of [*, obs] and [*, act] arrays
+  int params;                   // floats of one parameter block (W or G)
+  int off_w, off_g, off_x, off_h[2][3], off_adv, off_oldlp, off_vt, off_vold, off_act, off_loc,
+      off_val, off_dloc, off_dscale, off_dval, off_sd, off_misc, off_idx, off_red, total;
+  int t_off[kTensors], t_pitch[kTensors], t_rows[kTensors], t_cols[kTensors];
+
+  __host__ __device__ Carve(int O, int D) {
+    OP = O | 1;
+    DP = D | 1;
+    int o = 0;
+    for (int net = 0; net < 2; ++net) {
+      const int out = net == 0 ? D : 1;
+      const int rows[6] = {kH, kH, kH, kH, out, out};
+      const int cols[6] = {O, 1, kH, 1, kH, 1};
+      const int pitch[6] = {OP, 1, kHP, 1, kHP, 1};
+      for (int i = 0; i < 6; ++i) {
+        const int t = net * 6 + i;
+        t_off[t] = o;
+        t_pitch[t] = pitch[i];
+        t_rows[t] = rows[i];
+        t_cols[t] = cols[i];
+        o += rows[i] * pitch[i];
+      }
+    }
+    t_off[12] = o;
+    t_pitch[12] = 1;
+    t_rows[12] = D;
+    t_cols[12] = 1;
+    o += D;
+    params = (o + 3) & ~3;
+    o = 0;
+    off_w = o; o += params;
+    off_g = o; o += params;
+    off_x = o; o += kRows * OP;
+    for (int net = 0; net < 2; ++net)
+      for (int b = 0; b < 3; ++b) { off_h[net][b] = o; o += kRows * kHP; }
+    off_adv = o; o += kRows;
+    off_oldlp = o; o += kRows;
+    off_vt = o; o += kRows;
+    off_vold = o; o += kRows;
+    off_val = o; o += kRows;
+    off_dval = o; o += kRows;
+    off_act = o; o += kRows * DP;
+    off_loc = o; o += kRows * DP;
+    off_dloc = o; o += kRows * DP;
+    off_dscale = o; o += kRows * DP;
+    off_sd = o; o += kMaxAct;
+    off_misc = o; o += 16;                       // mean, denom, clip coefficient, Adam scalars
+    o = (o + 1) & ~1;
+    off_idx = o; o += 2 * kRows;                 // long long[64]
+    off_red = o; o += 2 * kAcc * 32;             // double[kAcc * 32]
+    total = o;
+  }
+  __host__ __device__ size_t bytes() const { return (size_t)total * sizeof(float); }
+};
+
+struct MlpArgs {
+  MlpTensor t[kTensors];
+  const void* obs;
+  int obs_f64, O, D;
+  const float *actions, *old_logp, *adv, *vtarg, *vold;
+  const long long* perm;
+  long long S, mb, step0;
+  int nsteps, nmb, normalize, has_clip;
+  double adv_eps, clip, vcoef, ecoef, max_norm, lr, beta1, beta2, eps;
+  float* losses;
+  float* stats;
+};
+
+// C(m, n) = sum_r A(r, m) * B(r, n) for m < M <= 64, n < N <= 64, by the 256 threads of one net.
+template <typename Epi>
+__device__ __forceinline__ void gemm64(const float* __restrict__ A, int a_sr, int a_sm, int M,
+                                       const float* __restrict__ B, int b_sr, int b_sn, int N,
+                                       int R, int t, Epi epi) {
+  const int tm = t >> 4, tn = t & 15;
+  int am[4], bn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = tm + 16 * i, n = tn + 16 * i;
+    am[i] = (m < M ? m : 0) * a_sm;
+    bn[i] = (n < N ? n : 0) * b_sn;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < R; ++r) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = A[r * a_sr + am[i]];
+      b[i] = B[r * b_sr + bn[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = tm + 16 * i, n = tn + 16 * j;
+      if (m < M && n < N) epi(m, n, acc[i][j]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const Carve c(a.O, a.D);
+  const int tid = threadIdx.x, net = tid >> 8, t = tid & (kNet - 1);
+  const int O = a.O, D = a.D, OP = c.OP, DP = c.DP;
+  float* W = sm + c.off_w;
+  float* G = sm + c.off_g;
+  float* X = sm + c.off_x;
+  float* H1 = sm + c.off_h[net][0];
+  float* H2 = sm + c.off_h[net][1];
+  float* Sb = sm + c.off_h[net][2];
+  float* s_adv = sm + c.off_adv;
+  float* s_oldlp = sm + c.off_oldlp;
+  float* s_vt = sm + c.off_vt;
+  float* s_vold = sm + c.off_vold;
+  float* s_val = sm + c.off_val;
+  float* s_dval = sm + c.off_dval;
+  float* s_act = sm + c.off_act;
+  float* s_loc = sm + c.off_loc;
+  float* s_dloc = sm + c.off_dloc;
+  float* s_dscale = sm + c.off_dscale;
+  float* s_sd = sm + c.off_sd;
+  float* misc = sm + c.off_misc;
+  long long* s_idx = reinterpret_cast<long long*>(sm + c.off_idx);
+  double* red = reinterpret_cast<double*>(sm + c.off_red);
+  // this net's tensors inside a parameter block
+  const int tb = net * 6;
+  const int oW1 = c.t_off[tb], ob1 = c.t_off[tb + 1], oW2 = c.t_off[tb + 2], ob2 = c.t_off[tb + 3];
+  const int oW3p = c.t_off[4], ob3p = c.t_off[5], oW3v = c.t_off[10], ob3v = c.t_off[11];
+  const int oLs = c.t_off[12];
+
+  // ---- parameters: global (dense) -> shared (padded)
+  for (int k = 0; k < kTensors; ++k) {
+    const int n = c.t_rows[k] * c.t_cols[k];
+    for (int e = tid; e < n; e += kThreads) {
+      const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
+      W[c.t_off[k] + r * c.t_pitch[k] + col] = a.t[k].w[e];
+    }
+  }
+  __syncthreads();
+
+  LossScalars ks;
+  ks.a2c = 0;
+  ks.has_clip = a.has_clip;
+  ks.lo = (float)(1.0 - a.clip);
+  ks.hi = (float)(1.0 + a.clip);
+  ks.vclip = (float)a.clip;
+  ks.vcoef = a.vcoef;
+  ks.ecoef = a.ecoef;
+  const float kLogSqrt2Pi = 0.918938533204672742f;
+  const float kHalfLog2PiE = 1.418938533204672742f;
+
+  for (int step = 0; step < a.nsteps; ++step) {
+    const int epoch = step / a.nmb, j = step - epoch * a.nmb;
+    const long long start = (long long)j * a.mb;
+    const long long count = a.S - start < a.mb ? a.S - start : a.mb;
+    const long long* rows_idx = a.perm + (long long)epoch * a.S + start;
+    ks.B = count;
+    ks.inv_b = 1.0f / (float)count;
+
+    // ---- minibatch moments of the advantages (float64), gradients <- 0, std = exp(logstd)
+    {
+      double s[2] = {0.0, 0.0};
+      if (a.normalize) {
+        for (long long i = tid; i < count; i += kThreads) {
+          const double x = (double)__ldg(a.adv + __ldg(rows_idx + i));
+          s[0] += x;
+          s[1] += x * x;
+        }
+      }
+      for (int e = tid; e < c.params; e += kThreads) G[e] = 0.f;
+      if (tid < D) s_sd[tid] = expf(W[oLs + tid]);
+      block_sum<2>(s, red);
+      if (tid == 0) {
+        float mean = 0.f, denom = 1.f;
+        if (a.normalize) {   // normalize_kernel's arithmetic (gae.cu)
+          const double n = (double)count, mean_d = s[0] / n;
+          double var_d = s[1] / n - mean_d * mean_d;
+          var_d = var_d > 0.0 ? var_d : 0.0;
+          mean = (float)mean_d;
+          denom = (float)((double)(float)sqrt(var_d) + a.adv_eps);
+        }
+        misc[0] = mean;
+        misc[1] = denom;
+      }
+      __syncthreads();
+    }
+    double acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+
+    for (long long chunk = 0; chunk < count; chunk += kRows) {
+      const int rows = (int)(count - chunk < kRows ? count - chunk : kRows);
+      // ---- gather this pass's rows
+      if (tid < kRows) {
+        const bool live = tid < rows;
+        const long long idx = live ? __ldg(rows_idx + chunk + tid) : 0;
+        s_idx[tid] = idx;
+        float adv = 0.f, olp = 0.f, vt = 0.f, vo = 0.f;
+        if (live) {
+          adv = __ldg(a.adv + idx);
+          if (a.normalize) adv = __fdiv_rn(__fsub_rn(adv, misc[0]), misc[1]);
+          olp = __ldg(a.old_logp + idx);
+          vt = __ldg(a.vtarg + idx);
+          vo = a.has_clip ? __ldg(a.vold + idx) : 0.f;
+        }
+        s_adv[tid] = adv;
+        s_oldlp[tid] = olp;
+        s_vt[tid] = vt;
+        s_vold[tid] = vo;
+      }
+      __syncthreads();
+      for (int e = tid; e < kRows * O; e += kThreads) {
+        const int r = e / O, k = e - r * O;
+        float x = 0.f;
+        if (r < rows) {
+          const long long g = s_idx[r] * O + k;
+          x = a.obs_f64 ? (float)__ldg(reinterpret_cast<const double*>(a.obs) + g)
+                        : __ldg(reinterpret_cast<const float*>(a.obs) + g);
+        }
+        X[r * OP + k] = x;
+      }
+      for (int e = tid; e < kRows * D; e += kThreads) {
+        const int r = e / D, k = e - r * D;
+        s_act[r * DP + k] = r < rows ? __ldg(a.actions + s_idx[r] * D + k) : 0.f;
+      }
+      __syncthreads();
+
+      // ---- forward: H1 = tanh(X W1^T + b1), H2 = tanh(H1 W2^T + b2)
+      gemm64(X, 1, OP, kRows, W + oW1, 1, OP, kH, O, t,
+             [&](int m, int n, float v) { H1[m * kHP + n] = tanhf(v + W[ob1 + n]); });
+      __syncthreads();
+      gemm64(H1, 1, kHP, kRows, W + oW2, 1, kHP, kH, kH, t,
+             [&](int m, int n, float v) { H2[m * kHP + n] = tanhf(v + W[ob2 + n]); });
+      __syncthreads();
+      // ---- heads: loc [64, D] from the policy trunk, value [64] from the value trunk
+      {
+        const float* H2p = sm + c.off_h[0][1];
+        const float* H2v = sm + c.off_h[1][1];
+        for (int o = tid; o < kRows * (D + 1); o += kThreads) {
+          const int r = o & (kRows - 1), col = o >> 6;
+          const float* h = (col < D ? H2p : H2v) + r * kHP;
+          const float* w = W + (col < D ? oW3p + col * kHP : oW3v);
+          float z = 0.f;
+#pragma unroll 8
+          for (int k = 0; k < kH; ++k) z = fmaf(h[k], w[k], z);
+          if (col < D) s_loc[r * DP + col] = z + W[ob3p + col];
+          else s_val[r] = z + W[ob3v];
+        }
+      }
+      __syncthreads();
+      // ---- PPO loss terms, one row per thread (K3's per-sample arithmetic)
+      if (tid < kRows) {
+        const bool live = tid < rows;
+        float* mu = s_loc + tid * DP;
+        const float* ac = s_act + tid * DP;
+        float* dl = s_dloc + tid * DP;
+        float* ds = s_dscale + tid * DP;
+        float dv = 0.f;
+        if (live) {
+          float lp = 0.f, h = 0.f;
+          for (int k = 0; k < D; ++k) {
+            const float sd = s_sd[k], diff = ac[k] - mu[k];
+            const float log_sd = logf(sd);
+            lp += -(diff * diff) / (2.f * (sd * sd)) - log_sd - kLogSqrt2Pi;
+            h += kHalfLog2PiE + log_sd;
+          }
+          acc[kEnt] += (double)h;
+          const float g = surrogate(lp, s_oldlp[tid], s_adv[tid], ks, acc);
+          const float ce = (float)ks.ecoef * ks.inv_b;
+          for (int k = 0; k < D; ++k) {
+            const float sd = s_sd[k], diff = ac[k] - mu[k];
+            const float inv_sd = 1.f / sd;
+            const float zsc = diff * inv_sd;
+            dl[k] = g * zsc * inv_sd;
+            ds[k] = g * (zsc * zsc - 1.f) * inv_sd - ce * inv_sd;
+          }
+          dv = (float)ks.vcoef * ks.inv_b * value_term(s_val[tid], s_vt[tid], s_vold[tid], ks, acc);
+        } else {
+          for (int k = 0; k < D; ++k) {
+            dl[k] = 0.f;
+            ds[k] = 0.f;
+          }
+        }
+        s_dval[tid] = dv;
+      }
+      __syncthreads();
+      // ---- head gradients: W3 / b3 of both nets, logstd
+      {
+        const float* H2p = sm + c.off_h[0][1];
+        const float* H2v = sm + c.off_h[1][1];
+        const int n_w = kH * (D + 1), n_all = n_w + 2 * D + 1;
+        for (int o = tid; o < n_all; o += kThreads) {
+          float s = 0.f;
+          if (o < n_w) {
+            const int k = o & (kH - 1), col = o >> 6;
+            if (col < D) {
+              for (int r = 0; r < kRows; ++r) s = fmaf(s_dloc[r * DP + col], H2p[r * kHP + k], s);
+              G[oW3p + col * kHP + k] += s;
+            } else {
+              for (int r = 0; r < kRows; ++r) s = fmaf(s_dval[r], H2v[r * kHP + k], s);
+              G[oW3v + k] += s;
+            }
+          } else if (o < n_w + D) {
+            const int col = o - n_w;
+            for (int r = 0; r < kRows; ++r) s += s_dloc[r * DP + col];
+            G[ob3p + col] += s;
+          } else if (o < n_w + 2 * D) {
+            const int col = o - n_w - D;   // d loss / d logstd = sum_rows dscale * std
+            for (int r = 0; r < kRows; ++r) s += s_dscale[r * DP + col];
+            G[oLs + col] += s * s_sd[col];
+          } else {
+            for (int r = 0; r < kRows; ++r) s += s_dval[r];
+            G[ob3v] += s;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- dZ2 = (dOut W3) * (1 - H2^2), in place over H2
+      for (int e = t; e < kRows * kH; e += kNet) {
+        const int r = e >> 6, k = e & (kH - 1);
+        float dh = 0.f;
+        if (net == 0) {
+          for (int col = 0; col < D; ++col) dh = fmaf(s_dloc[r * DP + col], W[oW3p + col * kHP + k], dh);
+        } else {
+          dh = s_dval[r] * W[oW3v + k];
+        }
+        const float h = H2[r * kHP + k];
+        H2[r * kHP + k] = dh * (1.f - h * h);
+      }
+      __syncthreads();
+      // ---- layer 2: dW2 += dZ2^T H1, db2, dZ1 = (dZ2 W2) * (1 - H1^2) -> Sb
+      gemm64(H2, kHP, 1, kH, H1, kHP, 1, kH, kRows, t,
+             [&](int m, int n, float v) { G[oW2 + m * kHP + n] += v; });
+      gemm64(H2, 1, kHP, kRows, W + oW2, kHP, 1, kH, kH, t, [&](int m, int n, float v) {
+        const float h = H1[m * kHP + n];
+        Sb[m * kHP + n] = v * (1.f - h * h);
+      });
+      if (t < kH) {
+        float s = 0.f;
+        for (int r = 0; r < kRows; ++r) s += H2[r * kHP + t];
+        G[ob2 + t] += s;
+      }
+      __syncthreads();
+      // ---- layer 1: dW1 += dZ1^T X, db1
+      gemm64(Sb, kHP, 1, kH, X, OP, 1, O, kRows, t,
+             [&](int m, int n, float v) { G[oW1 + m * OP + n] += v; });
+      if (t < kH) {
+        float s = 0.f;
+        for (int r = 0; r < kRows; ++r) s += Sb[r * kHP + t];
+        G[ob1 + t] += s;
+      }
+      __syncthreads();
+    }
+
+    // ---- the minibatch loss and its logged scalars
+    block_sum<kAcc>(acc, red);
+    if (tid == 0) {
+      write_loss(acc, ks, true, true, a.losses + step, a.stats + (size_t)step * DERL_LOSS_STATS);
+    }
+    // ---- clip_grad_norm_ (torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6),
+    // clamped to 1) and Adam (torch.optim.Adam, single-tensor formulas)
+    double sq[1] = {0.0};
+    for (int k = 0; k < kTensors; ++k) {
+      const int n = c.t_rows[k] * c.t_cols[k];
+      for (int e = tid; e < n; e += kThreads) {
+        const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
+        const double g = (double)G[c.t_off[k] + r * c.t_pitch[k] + col];
+        sq[0] += g * g;
+      }
+    }
+    __syncthreads();   // red is reused
+    block_sum<1>(sq, red);
+    if (tid == 0) {
+      float coef = 1.f;
+      if (a.max_norm >= 0.0) {
+        const float norm = (float)sqrt(sq[0]);
+        coef = fminf((float)a.max_norm / (norm + 1e-6f), 1.f);
+      }
+      const double stepno = (double)(a.step0 + step + 1);
+      const double bc1 = 1.0 - pow(a.beta1, stepno), bc2 = 1.0 - pow(a.beta2, stepno);
+      misc[2] = coef;
+      misc[3] = (float)(a.lr / bc1);       // step_size
+      misc[4] = (float)sqrt(bc2);          // bias_correction2_sqrt
+      a.stats[(size_t)step * DERL_LOSS_STATS + 10] = (float)sqrt(sq[0]);   // grad norm before clip
+    }
+    __syncthreads();
+    {
+      const float coef = misc[2], step_size = misc[3], bc2s = misc[4];
+      const float w1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
+      const float eps = (float)a.eps;
+      const bool apply_clip = a.max_norm >= 0.0;
+      for (int k = 0; k < kTensors; ++k) {
+        const int n = c.t_rows[k] * c.t_cols[k];
+        for (int e = tid; e < n; e += kThreads) {
+          const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
+          const int so = c.t_off[k] + r * c.t_pitch[k] + col;
+          float g = G[so];
+          if (apply_clip) g = g * coef;
+          float m = a.t[k].m[e], v = a.t[k].v[e];
+          m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+          v = v * b2 + w2 * (g * g);                  // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+          const float denom = sqrtf(v) / bc2s + eps;
+          W[so] = W[so] - step_size * (m / denom);    // addcdiv_(exp_avg, denom, -step_size)
+          a.t[k].m[e] = m;
+          a.t[k].v[e] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- parameters: shared -> global
+  for (int k = 0; k < kTensors; ++k) {
+    const int n = c.t_rows[k] * c.t_cols[k];
+    for (int e = tid; e < n; e += kThreads) {
+      const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
+      a.t[k].w[e] = W[c.t_off[k] + r * c.t_pitch[k] + col];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace derl
+
+using namespace derl;
+
+extern "C" size_t derl_b200_ppo_mlp_update_smem_bytes(int obs_dim, int act_dim) {
+  if (obs_dim < 1 || obs_dim > 64 || act_dim < 1 || act_dim > kMaxAct) return 0;
+  const size_t bytes = Carve(obs_dim, act_dim).bytes();
+  return bytes <= 227 * 1024 ? bytes : 0;
+}
+
+extern "C" int derl_b200_ppo_mlp_update(
+    float* const* params_dev, float* const* exp_avg_dev, float* const* exp_avg_sq_dev, int obs_dim,
+    int act_dim, const void* observations_dev, int obs_f64, const float* actions_dev,
+    const float* old_logp_dev, const float* advantages_dev, const float* value_targets_dev,
+    const float* old_values_dev, int64_t nsamples, const int64_t* perm_dev, int64_t nepochs,
+    int64_t minibatch, int normalize_advantages, double adv_epsilon, int has_clip, double cliprange,
+    double value_loss_coef, double entropy_coef, double max_grad_norm, double lr, double beta1,
+    double beta2, double adam_eps, int64_t adam_step, float* losses_dev, float* stats_dev,
+    void* stream) {
+  DERL_REQUIRE(params_dev && exp_avg_dev && exp_avg_sq_dev, "ppo_mlp_update: null tensor tables");
+  DERL_REQUIRE(observations_dev && actions_dev && old_logp_dev && advantages_dev &&
+                   value_targets_dev && perm_dev && losses_dev && stats_dev,
+               "ppo_mlp_update: null pointer");
+  DERL_REQUIRE(!has_clip || old_values_dev, "ppo_mlp_update: clipped value loss needs old values");
+  DERL_REQUIRE(nsamples >= 1 && nepochs >= 1 && minibatch >= 1 && minibatch <= nsamples,
+               "ppo_mlp_update: need 1 <= minibatch <= nsamples and nepochs >= 1 (got %lld, %lld, "
+               "%lld)", (long long)minibatch, (long long)nsamples, (long long)nepochs);
+  DERL_REQUIRE(adam_step >= 0 && lr >= 0.0 && beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 &&
+                   beta2 < 1.0 && adam_eps >= 0.0, "ppo_mlp_update: bad Adam hyper-parameters");
+  const size_t smem = derl_b200_ppo_mlp_update_smem_bytes(obs_dim, act_dim);
+  DERL_REQUIRE(smem != 0, "ppo_mlp_update: obs_dim %d / act_dim %d do not fit the shared-memory "
+               "plan (two 64-64 tanh MLPs, obs_dim <= ~40)", obs_dim, act_dim);
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  const long long nmb = (nsamples + minibatch - 1) / minibatch;
+  DERL_REQUIRE(nmb * nepochs < (1ll << 30), "ppo_mlp_update: too many optimiser steps");
+  MlpArgs a;
+  const Carve c(obs_dim, act_dim);
+  for (int k = 0; k < kTensors; ++k) {
+    DERL_REQUIRE(params_dev[k] && exp_avg_dev[k] && exp_avg_sq_dev[k],
+                 "ppo_mlp_update: tensor %d is NULL", k);
+    a.t[k] = MlpTensor{params_dev[k], exp_avg_dev[k], exp_avg_sq_dev[k], c.t_rows[k], c.t_cols[k],
+                       c.t_off[k], c.t_pitch[k]};
+  }
+  a.obs = observations_dev;
+  a.obs_f64 = obs_f64 ? 1 : 0;
+  a.O = obs_dim;
+  a.D = act_dim;
+  a.actions = actions_dev;
+  a.old_logp = old_logp_dev;
+  a.adv = advantages_dev;
+  a.vtarg = value_targets_dev;
+  a.vold = old_values_dev;
+  a.perm = reinterpret_cast<const long long*>(perm_dev);
+  a.S = nsamples;
+  a.mb = minibatch;
+  a.step0 = adam_step;
+  a.nsteps = (int)(nmb * nepochs);
+  a.nmb = (int)nmb;
+  a.normalize = normalize_advantages ? 1 : 0;
+  a.has_clip = has_clip ? 1 : 0;
+  a.adv_eps = adv_epsilon;
+  a.clip = cliprange;
+  a.vcoef = value_loss_coef;
+  a.ecoef = entropy_coef;
+  a.max_norm = max_grad_norm;
+  a.lr = lr;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = adam_eps;
+  a.losses = losses_dev;
+  a.stats = stats_dev;
+  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_mlp_update_kernel),
+                                        (int)smem))
+    return rc_attr;
+  ppo_mlp_update_kernel<<<1, kThreads, smem, as_stream(stream)>>>(a);
+  DERL_LAUNCH_CHECK("ppo_mlp_update_kernel");
+  return DERL_OK;
+}

@@ -30,28 +30,7 @@ __device__ __forceinline__ void finish_loss(double (&acc)[kAcc], const LossScala
   double tot[kAcc];
   final_sum<kAcc>(tot, workspace, scratch);
   if (threadIdx.x != 0) return;
-  const double b = (double)k.B;
-  const double pol = tot[kPol] / b, ent = tot[kEnt] / b, val = tot[kVal] / b;
-  double total = 0.0;
-  if (has_policy) total += pol - k.ecoef * ent;
-  if (has_value) total += k.vcoef * val;
-  // r_squared(targets, predictions) = 1 - mean((p - t)^2) / var_unbiased(p)   (alg/common.py:9-12);
-  // PPO passes predictions = values (ppo.py:94), A2C passes predictions = value_targets (a2c.py:62)
-  const double mean_v = tot[kV] / b;
-  const double mean_p = (k.a2c ? tot[kVt] : tot[kV]) / b;
-  const double var_v = ((k.a2c ? tot[kVtsq] : tot[kVsq]) - b * mean_p * mean_p) / (b - 1.0);
-  loss[0] = (float)total;
-  stats[0] = (float)total;
-  stats[1] = (float)pol;
-  stats[2] = (float)ent;
-  stats[3] = (float)val;
-  stats[4] = (float)(tot[kAdv] / b);
-  stats[5] = (float)(tot[kVt] / b);
-  stats[6] = (float)mean_v;
-  stats[7] = (float)(1.0 - (tot[kResid] / b) / var_v);
-  stats[8] = (float)(tot[kClipFrac] / b);
-  stats[9] = (float)(tot[kKl] / b);
-  for (int i = 10; i < DERL_LOSS_STATS; ++i) stats[i] = 0.f;
+  write_loss(tot, k, has_policy, has_value, loss, stats);
 }
 
 // Coalesced copy of `rows` consecutive rows of width `w` between global memory (dense) and a

@@ -719,3 +719,63 @@ def _a2c_gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
 
 
 a2c_loss_gaussian.register_autograd(_a2c_gauss_backward, setup_context=_a2c_gauss_setup)
+
+
+# --------------------------------------------------------------------------- K8: MLP PPO update
+@torch.library.custom_op("derl_b200::ppo_mlp_update",
+                         mutates_args=("params", "exp_avg", "exp_avg_sq"), device_types="cuda")
+def ppo_mlp_update(params: List[Tensor], exp_avg: List[Tensor], exp_avg_sq: List[Tensor],
+                   observations: Tensor, actions: Tensor, old_log_prob: Tensor,
+                   advantages: Tensor, value_targets: Tensor, old_values: Tensor, perm: Tensor,
+                   num_epochs: int, minibatch: int, normalize: bool, adv_epsilon: float,
+                   cliprange: Optional[float], value_loss_coef: float, entropy_coef: float,
+                   max_grad_norm: Optional[float], lr: float, beta1: float, beta2: float,
+                   adam_eps: float, adam_step: int) -> Tuple[Tensor, Tensor]:
+  """One whole PPO update (all epochs x minibatches) of the two-MLP actor-critic in one launch;
+  updates `params`, `exp_avg`, `exp_avg_sq` in place.  Returns (losses [nsteps], stats
+  [nsteps, 16]).  Tensor order: policy W1 b1 W2 b2 W3 b3, value W1 b1 W2 b2 W3 b3, logstd."""
+  _need(len(params) == 13 and len(exp_avg) == 13 and len(exp_avg_sq) == 13,
+        "ppo_mlp_update: 13 parameter / exp_avg / exp_avg_sq tensors expected")
+  _dense(observations, "observations", (torch.float32, torch.float64))
+  _need(observations.dim() == 2, "observations must be [S, obs_dim]")
+  size, obs_dim = observations.shape
+  act_dim = params[12].numel()
+  shapes = [(64, obs_dim), (64,), (64, 64), (64,), (act_dim, 64), (act_dim,),
+            (64, obs_dim), (64,), (64, 64), (64,), (1, 64), (1,), (act_dim,)]
+  for group, name in ((params, "params"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+    for i, (t, shape) in enumerate(zip(group, shapes)):
+      _dense(t, f"{name}[{i}]", (torch.float32,))
+      _need(tuple(t.shape) == shape, f"{name}[{i}] must have shape {shape}, got {tuple(t.shape)}")
+  _dense(actions, "actions", (torch.float32,))
+  _need(tuple(actions.shape) == (size, act_dim), "actions must be [S, act_dim]")
+  for name, t in (("log_prob", old_log_prob), ("advantages", advantages),
+                  ("value_targets", value_targets), ("values", old_values)):
+    _dense(t, name, (torch.float32,))
+    _need(t.numel() == size, f"{name} must have one element per sample")
+  _dense(perm, "perm", (torch.int64,))
+  _need(perm.numel() == num_epochs * size, "perm must hold num_epochs * S row indices")
+  _need(1 <= minibatch <= size and num_epochs >= 1, "bad minibatch size / epoch count")
+  nsteps = num_epochs * ((size + minibatch - 1) // minibatch)
+  losses = torch.empty(nsteps, dtype=torch.float32, device=observations.device)
+  stats = torch.empty((nsteps, _lib.LOSS_STATS), dtype=torch.float32, device=observations.device)
+  table = lambda ts: (_VP * 13)(*[t.data_ptr() for t in ts])
+  with _device_of(observations, "ppo_mlp_update"):
+    _lib.check(_lib.load().derl_b200_ppo_mlp_update(
+        table(params), table(exp_avg), table(exp_avg_sq), obs_dim, act_dim, _p(observations),
+        int(observations.dtype == torch.float64), _p(actions), _p(old_log_prob), _p(advantages),
+        _p(value_targets), _p(old_values), size, _p(perm), num_epochs, minibatch, int(normalize),
+        float(adv_epsilon), int(cliprange is not None), float(cliprange or 0.),
+        float(value_loss_coef), float(entropy_coef),
+        float(max_grad_norm) if max_grad_norm is not None else -1.0, float(lr), float(beta1),
+        float(beta2), float(adam_eps), int(adam_step), _p(losses), _p(stats),
+        _stream(observations)), "ppo_mlp_update")
+  return losses, stats
+
+
+@ppo_mlp_update.register_fake
+def _(params, exp_avg, exp_avg_sq, observations, actions, old_log_prob, advantages, value_targets,
+      old_values, perm, num_epochs, minibatch, normalize, adv_epsilon, cliprange, value_loss_coef,
+      entropy_coef, max_grad_norm, lr, beta1, beta2, adam_eps, adam_step):
+  nsteps = num_epochs * ((observations.shape[0] + minibatch - 1) // minibatch)
+  return (observations.new_empty(nsteps, dtype=torch.float32),
+          observations.new_empty((nsteps, _lib.LOSS_STATS), dtype=torch.float32))

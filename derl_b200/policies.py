@@ -99,6 +99,13 @@ class ActorCriticPolicy(Policy):
       log_prob = out["distribution"].log_prob(actions)
     return {"actions": _np(actions), "log_prob": _np(log_prob), "values": _np(out["values"])}
 
+  def value_tensor(self, observations):
+    """Critic values of `observations` as a tensor on the model's device, no graph, no host
+    round trip (extension: what GAE needs for its bootstrap, derl/runners/
+    trajectory_transforms.py:47-50, without the `.cpu().numpy()` synchronisation of `act`)."""
+    with torch.no_grad():
+      return self.model(observations)[-1]
+
   def _heads(self, observations):
     *dist_inputs, values = self.model(observations)
     if self.distribution is not None:

@@ -159,30 +159,34 @@ class IterateWithMinibatches(RunnerWrapper):
     perm = IterateWithMinibatches._upload(order, device)
     interactions.update(gather_minibatch(interactions, perm, 0, size, host_perm=order))
 
+  def minibatches(self, interactions):
+    """The epochs x minibatches of ONE rollout (the body of the reference's run loop, :52-62)."""
+    size = self._sample_size(interactions)
+    device = next((v.device for v in interactions.values()
+                   if isinstance(v, torch.Tensor) and v.is_cuda), None)
+    if device is None:
+      raise TypeError("IterateWithMinibatches needs the rollout resident on the GPU "
+                      "(wrap the runner in TransformInteractions first)")
+    order, perm, perm_ready = None, None, None
+    for _ in range(self.num_epochs):
+      if self.shuffle_before_epoch:
+        draw = np.random.permutation(size)                  # same RNG stream as :46
+        order = draw if order is None else order[draw]      # compose: shuffles were in place
+        perm = self._upload(order, device)
+        perm_ready = torch.cuda.current_stream(device).record_event()
+      elif perm is None:
+        order = np.arange(size)
+        perm = self._upload(order, device)
+        perm_ready = torch.cuda.current_stream(device).record_event()
+      mbsize = size // self.num_minibatches
+      for start in range(0, size, mbsize):
+        count = min(start + mbsize, size) - start
+        yield gather_minibatch(interactions, perm, start, count, host_perm=order,
+                               perm_ready=perm_ready, fused_gather=self.fused_gather)
+
   def run(self, obs=None):
     for interactions in self.runner.run(obs=obs):
-      size = self._sample_size(interactions)
-      device = next((v.device for v in interactions.values()
-                     if isinstance(v, torch.Tensor) and v.is_cuda), None)
-      if device is None:
-        raise TypeError("IterateWithMinibatches needs the rollout resident on the GPU "
-                        "(wrap the runner in TransformInteractions first)")
-      order, perm, perm_ready = None, None, None
-      for _ in range(self.num_epochs):
-        if self.shuffle_before_epoch:
-          draw = np.random.permutation(size)                  # same RNG stream as :46
-          order = draw if order is None else order[draw]      # compose: shuffles were in place
-          perm = self._upload(order, device)
-          perm_ready = torch.cuda.current_stream(device).record_event()
-        elif perm is None:
-          order = np.arange(size)
-          perm = self._upload(order, device)
-          perm_ready = torch.cuda.current_stream(device).record_event()
-        mbsize = size // self.num_minibatches
-        for start in range(0, size, mbsize):
-          count = min(start + mbsize, size) - start
-          yield gather_minibatch(interactions, perm, start, count, host_perm=order,
-                                 perm_ready=perm_ready, fused_gather=self.fused_gather)
+      yield from self.minibatches(interactions)
 
 
 def ppo_runner_wrap(runner, gamma=0.99, lambda_=0.95, num_epochs=3, num_minibatches=4,

@@ -65,6 +65,9 @@ class GAE:
     state = trajectory["state"]
     if state.get("latest_values") is not None:   # EnvRunner(resident_device=): already evaluated
       return state["latest_values"]
+    value_tensor = getattr(self.policy, "value_tensor", None)
+    if value_tensor is not None and state.get("policy_state", None) is None:
+      return value_tensor(state["latest_observations"])   # stays on the device: no sync
     return self.policy.act(state["latest_observations"], state=state.get("policy_state", None),
                            update_state=False)["values"]
 

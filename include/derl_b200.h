@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-/* 2: derl_b200_stem_conv_relu / derl_b200_stem_backward gained `rows_dev` (fused minibatch gather). */
-#define DERL_B200_ABI_VERSION 2
+/* 2: derl_b200_stem_conv_relu / derl_b200_stem_backward gained `rows_dev` (fused minibatch gather).
+ * 3: derl_b200_ppo_mlp_update (whole PPO update of the MuJoCo-shaped actor-critic in one launch). */
+#define DERL_B200_ABI_VERSION 3
 
 enum {
   DERL_OK = 0,
@@ -299,6 +300,41 @@ int derl_b200_gae_host(const void* rewards_host, int rewards_f64, const float* v
                        const uint8_t* resets_host, const float* last_value_host, int64_t T,
                        int64_t N, double gamma, double lambda, int normalize, double epsilon,
                        float* advantages_host, float* value_targets_host, void* stream);
+
+/* ------------------------------------------------------------------ K8: whole PPO update, MLP actor-critic
+ * One launch = every epoch and minibatch of one rollout's PPO update for the reference's
+ * MuJoCo model (derl/models.py:224-271: two tanh MLPs obs -> 64 -> 64 -> {act_dim, 1} plus a
+ * state-independent logstd): permutation gather (derl/runners/onpolicy.py:43-62), minibatch
+ * advantage normalisation (trajectory_transforms.py:89-92), forward, PPOLoss with the diagonal
+ * Gaussian head (derl/alg/ppo.py:24-108), backward, clip_grad_norm_ and the Adam step
+ * (derl/alg/common.py:56-78; torch.optim.Adam single-tensor formulas, amsgrad / weight decay off).
+ * A persistent single-CTA kernel with parameters and gradients in shared memory: at 64-row
+ * minibatches the reference's 320 optimiser steps per update are launch-latency work.
+ *
+ *   params_dev / exp_avg_dev / exp_avg_sq_dev: 13 device pointers each, float32, dense, in the
+ *     order  policy {W1 [64,obs], b1 [64], W2 [64,64], b2 [64], W3 [act,64], b3 [act]},
+ *            value  {W1, b1, W2, b2, W3 [1,64], b3 [1]},  logstd [act];  updated IN PLACE
+ *   observations [nsamples, obs_dim] float64 (obs_f64 = 1; cast to float32 like the reference's
+ *     collocate_inputs, derl/models.py:83-87) or float32; actions [nsamples, act_dim] float32;
+ *     old_logp, advantages (NOT yet normalised), value_targets, old_values [nsamples] float32
+ *   perm_dev [nepochs * nsamples] int64: epoch e's minibatch j is rows
+ *     perm[e * nsamples + j * minibatch ...] (a trailing short minibatch when nsamples is not a
+ *     multiple, like range(0, S, mbsize) in onpolicy.py:56); indices are trusted
+ *   max_grad_norm < 0: no clipping;  adam_step: optimiser steps already taken (state["step"])
+ *   losses_dev [nsteps] float32, stats_dev [nsteps * DERL_LOSS_STATS] float32 out
+ *     (nsteps = nepochs * ceil(nsamples / minibatch); stats as in K3, [10] = gradient norm
+ *     before clipping).
+ * derl_b200_ppo_mlp_update_smem_bytes: dynamic shared memory the shape needs, 0 = unsupported. */
+size_t derl_b200_ppo_mlp_update_smem_bytes(int obs_dim, int act_dim);
+int derl_b200_ppo_mlp_update(
+    float* const* params_dev, float* const* exp_avg_dev, float* const* exp_avg_sq_dev, int obs_dim,
+    int act_dim, const void* observations_dev, int obs_f64, const float* actions_dev,
+    const float* old_logp_dev, const float* advantages_dev, const float* value_targets_dev,
+    const float* old_values_dev, int64_t nsamples, const int64_t* perm_dev, int64_t nepochs,
+    int64_t minibatch, int normalize_advantages, double adv_epsilon, int has_clip, double cliprange,
+    double value_loss_coef, double entropy_coef, double max_grad_norm, double lr, double beta1,
+    double beta2, double adam_eps, int64_t adam_step, float* losses_dev, float* stats_dev,
+    void* stream);
 
 #ifdef __cplusplus
 }

@@ -652,13 +652,37 @@ def test_full_ppo_update_matches_reference_losses(golden, name, kind):
 
 
 # Tolerances of the benchmarked (default `bench.py`) arithmetic against the reference's float32
-# losses: TF32 tensor-core conv/GEMM (10-bit mantissa operands, fp32 accumulation) plus the INT8
-# two-digit stem kernels K6/K7 (operand residual <= 1/508 of a channel's scale, below TF32's).
-# The loss is a mean of O(1) per-sample terms; eight Adam steps (lr 2.5e-4, sign-like updates)
-# compound the difference.  Measured on B200 (profiles/r02_tf32_parity.txt): worst loss deviation
-# 2.6e-4 relative, parameter-sum deviation 1.1e-6 of sum|p|; the bounds below are ~4x that.
-TF32_LOSS_RTOL = 1e-3
-TF32_PARAM_SUM_TOL = 5e-6   # of sum |p| (25771): the sum itself cancels to -13.4
+# losses.  Two different things are bounded:
+#  * the FIRST loss is a pure forward pass on identical parameters — it measures the arithmetic
+#    itself: TF32 tensor-core conv/GEMM (10-bit mantissa operands, fp32 accumulation) plus the
+#    INT8 two-digit stem K6 (operand residual <= 1/508 of a channel's scale).  Measured on B200
+#    (profiles/r02_tf32_parity.txt): 9e-5 relative; bound 5e-4.
+#  * later losses follow 1..7 Adam steps.  Adam's update lr * m / (sqrt(v) + eps) is sign-like in
+#    its first steps, so a 1e-3 relative gradient perturbation (TF32's operand rounding) moves
+#    1.7 M parameters by O(lr) in slightly different directions and the 12-sample minibatch
+#    losses drift by ~1 % — for cuDNN/cuBLAS TF32 alone (custom_stem off) just as for the
+#    default path with K6/K7 (measured side by side in the same file).  Bound 3e-2, and the
+#    default path must not drift more than 2x what the TF32 library path does.
+TF32_FIRST_LOSS_RTOL = 5e-4
+TF32_LOSS_RTOL = 3e-2
+TF32_PARAM_SUM_TOL = 2e-5   # of sum |p| (25771): the sum itself cancels to -13.4
+
+
+def _tf32_update(golden, custom_stem, fused_gather):
+  g = golden("live_update_atari.npz")
+  torch.backends.cuda.matmul.allow_tf32 = True
+  torch.backends.cudnn.allow_tf32 = True
+  saved = d.NatureCNNBase.custom_stem
+  d.NatureCNNBase.custom_stem = custom_stem
+  try:
+    losses, model = run_golden_update(g, "atari", micro_batch=5, fused_gather=fused_gather)
+  finally:
+    d.NatureCNNBase.custom_stem = saved
+    torch.backends.cuda.matmul.allow_tf32 = False
+  rel = np.abs(np.asarray(losses) - g["losses"]) / np.abs(g["losses"])
+  final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+  dsum = abs(final.sum().item() - float(g["final_param_sum"])) / float(g["final_param_abs_sum"])
+  return rel, dsum
 
 
 @pytest.mark.parametrize("fused_gather", [False, True])
@@ -668,23 +692,19 @@ def test_benchmarked_configuration_tracks_the_fp32_reference_losses(golden, fuse
   (ragged chunks: 12-row minibatches in chunks of 5), optionally the fused gather — run on the
   reference's golden rollouts and compared with the losses the reference's float32 CPU classes
   produced (tests/golden/live_update_atari.npz).  This pins the benchmarked arithmetic end to
-  end against the oracle with a stated tolerance."""
+  end against the oracle with stated tolerances (see the comment above)."""
   assert d.NatureCNNBase.custom_stem and d.NatureCNNBase.space_to_depth_hidden
-  torch.backends.cuda.matmul.allow_tf32 = True
-  torch.backends.cudnn.allow_tf32 = True
   launches = _lib.launch_count()
-  g = golden("live_update_atari.npz")
-  try:
-    losses, model = run_golden_update(g, "atari", micro_batch=5, fused_gather=fused_gather)
-  finally:
-    torch.backends.cuda.matmul.allow_tf32 = False
+  rel, dsum = _tf32_update(golden, True, fused_gather)
   assert _lib.launch_count() - launches >= 8 * 3 * 2, "K6/K7 did not run"
-  rel = np.abs(np.asarray(losses) - g["losses"]) / np.abs(g["losses"])
-  final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
-  dsum = abs(final.sum().item() - float(g["final_param_sum"])) / float(g["final_param_abs_sum"])
-  print(f"\n[tf32 parity fused_gather={fused_gather}] max loss rel dev {rel.max():.3e} "
-        f"(per step {np.array2string(rel, precision=2)}), param-sum dev {dsum:.3e} of sum|p|")
-  np.testing.assert_allclose(losses, g["losses"], rtol=TF32_LOSS_RTOL, atol=0)
+  lib_rel, lib_dsum = _tf32_update(golden, False, False)   # cuDNN/cuBLAS TF32 only, no K6/K7
+  print(f"\n[tf32 parity] default path (fused_gather={fused_gather}): loss rel dev per step "
+        f"{np.array2string(rel, precision=2)}, param-sum dev {dsum:.2e} of sum|p|\n"
+        f"[tf32 parity] TF32 library path (no K6/K7):      loss rel dev per step "
+        f"{np.array2string(lib_rel, precision=2)}, param-sum dev {lib_dsum:.2e} of sum|p|")
+  assert rel[0] <= TF32_FIRST_LOSS_RTOL, rel
+  assert rel.max() <= TF32_LOSS_RTOL, rel
+  assert rel.max() <= 2.0 * max(lib_rel.max(), 5e-3), (rel, lib_rel)
   assert dsum <= TF32_PARAM_SUM_TOL, dsum
 
 
@@ -1189,3 +1209,143 @@ def test_env_runner_resident_on_cuda_feeds_gae_without_a_second_forward():
     assert np.array_equal(targets.cpu().numpy(), want_targets)
   finally:
     torch.backends.cudnn.allow_tf32 = True
+
+
+# =============================================================================== K8: fused MLP update
+class _ArraySource:
+  """EnvRunner-shaped source over prepared rollouts (unbatched env: nenvs None)."""
+
+  def __init__(self, rollouts, policy, horizon):
+    self.rollouts, self.policy, self.horizon = rollouts, policy, horizon
+    self.env = type("E", (), {"nenvs": None, "unwrapped": property(lambda s: s)})()
+    self.nenvs, self.step_count = None, 0
+    self.nsteps = horizon * len(rollouts)
+
+  def is_exhausted(self):
+    return self.step_count >= self.nsteps
+
+  def __len__(self):
+    return self.nsteps
+
+  def run(self, obs=None):
+    for data in self.rollouts:
+      self.step_count += self.horizon
+      yield {k: (dict(v) if k == "state" else v) for k, v in data.items()}
+
+
+def _mujoco_alg(rollouts, obs_dim, act_dim, epochs, nmb, lr=3e-4, hp=None, max_grad_norm=.5):
+  torch.manual_seed(0)
+  model = d.MuJoCoModel(obs_dim, [act_dim, 1])
+  policy = d.ActorCriticPolicy(model)
+  horizon = rollouts[0]["rewards"].shape[0]
+  runner = d.ppo_runner_wrap(_ArraySource(rollouts, policy, horizon), num_epochs=epochs,
+                             num_minibatches=nmb)
+  optimizer = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-5)
+  alg = d.PPO(runner, d.Trainer(optimizer, max_grad_norm=max_grad_norm),
+              **(hp or dict(cliprange=.2, value_loss_coef=.25, entropy_coef=0.)))
+  return alg, model, optimizer
+
+
+def test_fused_mlp_update_matches_the_reference_golden_update(golden):
+  """K8 (one launch per rollout: gather, normalise, forward, PPO loss, backward, clip, Adam for
+  every epoch x minibatch) through `PPO.learn()` on the reference's golden MuJoCo-shaped
+  rollouts: the 16 losses the reference's classes produced and its final parameters, at the
+  tolerance of the per-minibatch GPU path (rtol 1e-4: float32 summation order differs from the
+  CPU's, and the difference compounds over Adam steps)."""
+  from derl_b200.alg.fused_mlp import FusedMLPUpdate
+  g = golden("live_update_mujoco.npz")
+  rollouts = []
+  for r in range(int(g["nrollouts"])):
+    data = {k: g[f"r{r}_{k}"] for k in ("observations", "actions", "log_prob", "values",
+                                         "rewards", "resets")}
+    data["state"] = dict(latest_observations=g[f"r{r}_latest_observations"])
+    rollouts.append(data)
+  alg, model, optimizer = _mujoco_alg(rollouts, g["r0_observations"].shape[-1],
+                                      g["r0_actions"].shape[-1], int(g["epochs"]), int(g["nmb"]),
+                                      lr=float(g["lr"]),
+                                      hp=dict(cliprange=float(g["cliprange"]),
+                                              value_loss_coef=float(g["value_loss_coef"]),
+                                              entropy_coef=float(g["entropy_coef"])))
+  assert FusedMLPUpdate.plan(alg) is not None, "the stock MuJoCo pipeline must take the fused path"
+  np.random.seed(int(g["seed"]))
+  launches = _lib.launch_count()
+  losses = []
+  source = alg.runner.unwrapped
+  for r in range(len(rollouts)):   # learn() one rollout at a time to collect every loss
+    source.nsteps = source.horizon * (r + 1)
+    source.rollouts = rollouts[r:r + 1]
+    alg.learn(progress=False)
+    losses += alg.last_losses.cpu().tolist()
+  per_update = int(g["epochs"]) * int(g["nmb"])
+  assert len(losses) == per_update * len(rollouts)
+  # per rollout: GAE + the one update kernel (the bootstrap forward is library code)
+  assert _lib.launch_count() - launches == 2 * len(rollouts)
+  np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
+  state = model.state_dict()
+  for key, val in state.items():
+    np.testing.assert_allclose(val.cpu().numpy(), g["final_" + key], rtol=1e-4, atol=1e-6,
+                               err_msg=key)
+  assert alg.trainer.step_count == len(losses) and alg.loss_fn.call_count == len(losses)
+  steps = {float(s["step"]) for s in optimizer.state.values()}
+  assert steps == {float(len(losses))}
+  assert all(p.grad is None for p in model.parameters())
+
+
+@pytest.mark.parametrize("size,nmb,epochs,obs_dim,act_dim,obs_dtype", [
+    (384, 4, 2, 17, 6, np.float64),    # 96-row minibatches: a full and a partial 64-row pass
+    (100, 3, 2, 11, 3, np.float32),    # ragged: 33, 33, 33, 1
+    (2048, 32, 2, 26, 8, np.float64),  # BASELINE configs[1] minibatch shape, pybullet-sized obs
+])
+def test_fused_mlp_update_equals_the_per_minibatch_path(size, nmb, epochs, obs_dim, act_dim,
+                                                        obs_dtype):
+  """Same seeds, same rollout: `PPO.learn()` on the fused kernel vs minibatch-by-minibatch
+  `alg.step` (gather kernels + library MLP + K3 + torch clip/Adam).  The two are float32
+  evaluations of the same formulas in different summation orders: the first loss (identical
+  parameters) agrees to 1e-5, later losses and the final parameters to what a few Adam steps
+  of that noise give (1e-3 of the loss; 2e-5 absolute on parameters of O(0.1-1))."""
+  rng = np.random.RandomState(size)
+  rollout = dict(observations=rng.standard_normal((size, obs_dim)).astype(obs_dtype),
+                 actions=rng.standard_normal((size, act_dim)).astype(np.float32),
+                 log_prob=(rng.standard_normal(size) * .1 - 1.4 * act_dim).astype(np.float32),
+                 values=(rng.standard_normal((size, 1)) * .1).astype(np.float32),
+                 rewards=rng.standard_normal(size), resets=rng.rand(size) < .01,
+                 state=dict(latest_observations=rng.standard_normal(obs_dim).astype(obs_dtype)))
+  results = []
+  for fused in (True, False):
+    alg, model, _ = _mujoco_alg([rollout], obs_dim, act_dim, epochs, nmb)
+    np.random.seed(3)
+    if fused:
+      alg.learn(progress=False)
+      losses = alg.last_losses.cpu().numpy()
+    else:
+      losses = np.asarray([alg.step(batch).item() for batch in alg.runner.run()])
+    results.append((losses, [p.detach().cpu().numpy() for p in model.parameters()]))
+  (fl, fp), (el, ep) = results
+  assert fl.shape == el.shape
+  np.testing.assert_allclose(fl[0], el[0], rtol=1e-5)
+  np.testing.assert_allclose(fl, el, rtol=1e-3, atol=1e-5)
+  for a, b in zip(fp, ep):
+    np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_fused_mlp_plan_rejects_what_it_does_not_model():
+  """Anything but the stock pipeline falls back to the per-minibatch path."""
+  from derl_b200.alg.fused_mlp import FusedMLPUpdate
+  rng = np.random.RandomState(0)
+  rollout = dict(observations=rng.standard_normal((64, 5)), rewards=rng.standard_normal(64))
+  alg, model, opt = _mujoco_alg([rollout], 5, 2, 2, 4)
+  assert FusedMLPUpdate.plan(alg) is not None
+  alg.trainer.micro_batch = 16
+  assert FusedMLPUpdate.plan(alg) is None
+  alg.trainer.micro_batch = None
+  opt.param_groups[0]["weight_decay"] = 0.1
+  assert FusedMLPUpdate.plan(alg) is None
+  opt.param_groups[0]["weight_decay"] = 0
+  alg.runner.runner.fused_gather = True
+  assert FusedMLPUpdate.plan(alg) is None
+  alg.runner.runner.fused_gather = False
+  wide = d.MuJoCoModel(5, [2, 1], mlp=lambda i, o: d.MLP(i, o, hidden_features=(32, 32)))
+  alg.model = wide
+  assert FusedMLPUpdate.plan(alg) is None
+  assert _lib.load().derl_b200_ppo_mlp_update_smem_bytes(376, 17) == 0   # Humanoid: too wide
+  assert _lib.load().derl_b200_ppo_mlp_update_smem_bytes(17, 6) > 0
