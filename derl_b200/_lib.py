@@ -56,10 +56,11 @@ SIGNATURES = {
     "derl_b200_stem_backward": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _size,
                                       _ptr]),
     "derl_b200_ppo_mlp_update_smem_bytes": (_size, [_int, _int]),
+    "derl_b200_ppo_mlp_update_workspace_bytes": (_size, [_int, _int]),
     "derl_b200_ppo_mlp_update": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _int, _ptr, _ptr, _ptr,
                                         _ptr, _ptr, _i64, _ptr, _i64, _i64, _int, _f64, _int, _f64,
                                         _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _ptr, _ptr,
-                                        _ptr]),
+                                        _ptr, _size, _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,
                                   _f64, _ptr, _ptr, _ptr]),
 }

@@ -13,7 +13,8 @@
 // whole update is one persistent CTA: parameters and their gradients live in shared memory for
 // all 320 steps (odd row pitches make every GEMM operand access conflict-free), a step is
 // ~30 k cycles of fp32 FMA work, and Adam's moment vectors are the only per-step global traffic
-// (88 KB, L2-resident).  fp32 FMA on CUDA cores, not tensor cores: the contract is the
+// (88 KB, L2-resident, kept in the same padded layout as the shared parameter block so that the
+// update loop is one division-free sweep with independent loads).  fp32 FMA on CUDA cores, not tensor cores: the contract is the
 // reference's float32 (rtol 1e-5 on the loss), and [64 x 64 x 64] GEMMs on one SM are
 // latency-, not throughput-bound.
 //
@@ -113,6 +114,8 @@ struct MlpArgs {
   double adv_eps, clip, vcoef, ecoef, max_norm, lr, beta1, beta2, eps;
   float* losses;
   float* stats;
+  float* ws_m;     // Adam moments in the PADDED shared-memory layout (Carve::params floats each):
+  float* ws_v;     // element e of the workspace belongs to element e of the parameter block
 };
 
 // C(m, n) = sum_r A(r, m) * B(r, n) for m < M <= 64, n < N <= 64, by the 256 threads of one net.
@@ -186,12 +189,21 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
   const int oW3p = c.t_off[4], ob3p = c.t_off[5], oW3v = c.t_off[10], ob3v = c.t_off[11];
   const int oLs = c.t_off[12];
 
-  // ---- parameters: global (dense) -> shared (padded)
+  // ---- parameters: global (dense) -> shared (padded); Adam moments -> padded workspace
+  for (int e = tid; e < c.params; e += kThreads) {   // padding entries: defined and inert
+    W[e] = 0.f;
+    a.ws_m[e] = 0.f;
+    a.ws_v[e] = 0.f;
+  }
+  __syncthreads();
   for (int k = 0; k < kTensors; ++k) {
     const int n = c.t_rows[k] * c.t_cols[k];
     for (int e = tid; e < n; e += kThreads) {
       const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
-      W[c.t_off[k] + r * c.t_pitch[k] + col] = a.t[k].w[e];
+      const int so = c.t_off[k] + r * c.t_pitch[k] + col;
+      W[so] = a.t[k].w[e];
+      a.ws_m[so] = a.t[k].m[e];
+      a.ws_v[so] = a.t[k].v[e];
     }
   }
   __syncthreads();
@@ -225,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
           s[1] += x * x;
         }
       }
-      for (int e = tid; e < c.params; e += kThreads) G[e] = 0.f;
+      if (step == 0) {
+        for (int e = tid; e < c.params; e += kThreads) G[e] = 0.f;   // later steps: Adam re-zeroes
+      }
       if (tid < D) s_sd[tid] = expf(W[oLs + tid]);
       block_sum<2>(s, red);
       if (tid == 0) {
@@ -418,13 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
     // ---- clip_grad_norm_ (torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6),
     // clamped to 1) and Adam (torch.optim.Adam, single-tensor formulas)
     double sq[1] = {0.0};
-    for (int k = 0; k < kTensors; ++k) {
-      const int n = c.t_rows[k] * c.t_cols[k];
-      for (int e = tid; e < n; e += kThreads) {
-        const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
-        const double g = (double)G[c.t_off[k] + r * c.t_pitch[k] + col];
-        sq[0] += g * g;
-      }
+    for (int e = tid; e < c.params; e += kThreads) {   // padding entries of G are zero
+      const double g = (double)G[e];
+      sq[0] += g * g;
     }
     __syncthreads();   // red is reused
     block_sum<1>(sq, red);
@@ -447,21 +457,21 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
       const float w1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
       const float eps = (float)a.eps;
       const bool apply_clip = a.max_norm >= 0.0;
-      for (int k = 0; k < kTensors; ++k) {
-        const int n = c.t_rows[k] * c.t_cols[k];
-        for (int e = tid; e < n; e += kThreads) {
-          const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
-          const int so = c.t_off[k] + r * c.t_pitch[k] + col;
-          float g = G[so];
-          if (apply_clip) g = g * coef;
-          float m = a.t[k].m[e], v = a.t[k].v[e];
-          m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
-          v = v * b2 + w2 * (g * g);                  // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-          const float denom = sqrtf(v) / bc2s + eps;
-          W[so] = W[so] - step_size * (m / denom);    // addcdiv_(exp_avg, denom, -step_size)
-          a.t[k].m[e] = m;
-          a.t[k].v[e] = v;
-        }
+      // over the padded block: padding entries have g = m = v = 0 and stay 0
+      float* __restrict__ wm = a.ws_m;
+      float* __restrict__ wv = a.ws_v;
+#pragma unroll 4
+      for (int e = tid; e < c.params; e += kThreads) {
+        float g = G[e];
+        G[e] = 0.f;                                   // ready for the next step's accumulation
+        if (apply_clip) g = g * coef;
+        float m = wm[e], v = wv[e];
+        m = m + w1 * (g - m);                         // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * b2 + w2 * (g * g);                    // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = sqrtf(v) / bc2s + eps;
+        W[e] = W[e] - step_size * (m / denom);        // addcdiv_(exp_avg, denom, -step_size)
+        wm[e] = m;
+        wv[e] = v;
       }
     }
     __syncthreads();
@@ -472,7 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
     const int n = c.t_rows[k] * c.t_cols[k];
     for (int e = tid; e < n; e += kThreads) {
       const int r = e / c.t_cols[k], col = e - r * c.t_cols[k];
-      a.t[k].w[e] = W[c.t_off[k] + r * c.t_pitch[k] + col];
+      const int so = c.t_off[k] + r * c.t_pitch[k] + col;
+      a.t[k].w[e] = W[so];
+      a.t[k].m[e] = a.ws_m[so];   // written by another thread of this CTA in the Adam loop: the
+      a.t[k].v[e] = a.ws_v[so];   // __syncthreads() that ends the last step orders the two
     }
   }
 }
@@ -481,6 +494,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
 }  // namespace derl
 
 using namespace derl;
+
+extern "C" size_t derl_b200_ppo_mlp_update_workspace_bytes(int obs_dim, int act_dim) {
+  if (obs_dim < 1 || obs_dim > 64 || act_dim < 1 || act_dim > kMaxAct) return 0;
+  return 2 * (size_t)Carve(obs_dim, act_dim).params * sizeof(float);
+}
 
 extern "C" size_t derl_b200_ppo_mlp_update_smem_bytes(int obs_dim, int act_dim) {
   if (obs_dim < 1 || obs_dim > 64 || act_dim < 1 || act_dim > kMaxAct) return 0;
@@ -496,7 +514,7 @@ extern "C" int derl_b200_ppo_mlp_update(
     int64_t minibatch, int normalize_advantages, double adv_epsilon, int has_clip, double cliprange,
     double value_loss_coef, double entropy_coef, double max_grad_norm, double lr, double beta1,
     double beta2, double adam_eps, int64_t adam_step, float* losses_dev, float* stats_dev,
-    void* stream) {
+    void* workspace_dev, size_t workspace_bytes, void* stream) {
   DERL_REQUIRE(params_dev && exp_avg_dev && exp_avg_sq_dev, "ppo_mlp_update: null tensor tables");
   DERL_REQUIRE(observations_dev && actions_dev && old_logp_dev && advantages_dev &&
                    value_targets_dev && perm_dev && losses_dev && stats_dev,
@@ -510,6 +528,11 @@ extern "C" int derl_b200_ppo_mlp_update(
   const size_t smem = derl_b200_ppo_mlp_update_smem_bytes(obs_dim, act_dim);
   DERL_REQUIRE(smem != 0, "ppo_mlp_update: obs_dim %d / act_dim %d do not fit the shared-memory "
                "plan (two 64-64 tanh MLPs, obs_dim <= ~40)", obs_dim, act_dim);
+  if (workspace_dev == nullptr ||
+      workspace_bytes < derl_b200_ppo_mlp_update_workspace_bytes(obs_dim, act_dim)) {
+    set_error("ppo_mlp_update: workspace %zu B too small", workspace_bytes);
+    return DERL_E_WORKSPACE;
+  }
   int rc = require_device();
   if (rc != DERL_OK) return rc;
   const long long nmb = (nsamples + minibatch - 1) / minibatch;
@@ -550,6 +573,8 @@ extern "C" int derl_b200_ppo_mlp_update(
   a.eps = adam_eps;
   a.losses = losses_dev;
   a.stats = stats_dev;
+  a.ws_m = reinterpret_cast<float*>(workspace_dev);
+  a.ws_v = a.ws_m + c.params;
   if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_mlp_update_kernel),
                                         (int)smem))
     return rc_attr;

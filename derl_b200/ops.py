@@ -759,6 +759,9 @@ def ppo_mlp_update(params: List[Tensor], exp_avg: List[Tensor], exp_avg_sq: List
   losses = torch.empty(nsteps, dtype=torch.float32, device=observations.device)
   stats = torch.empty((nsteps, _lib.LOSS_STATS), dtype=torch.float32, device=observations.device)
   table = lambda ts: (_VP * 13)(*[t.data_ptr() for t in ts])
+  lib = _lib.load()
+  ws_bytes = lib.derl_b200_ppo_mlp_update_workspace_bytes(obs_dim, act_dim)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=observations.device)
   with _device_of(observations, "ppo_mlp_update"):
     _lib.check(_lib.load().derl_b200_ppo_mlp_update(
         table(params), table(exp_avg), table(exp_avg_sq), obs_dim, act_dim, _p(observations),
@@ -767,7 +770,7 @@ def ppo_mlp_update(params: List[Tensor], exp_avg: List[Tensor], exp_avg_sq: List
         float(adv_epsilon), int(cliprange is not None), float(cliprange or 0.),
         float(value_loss_coef), float(entropy_coef),
         float(max_grad_norm) if max_grad_norm is not None else -1.0, float(lr), float(beta1),
-        float(beta2), float(adam_eps), int(adam_step), _p(losses), _p(stats),
+        float(beta2), float(adam_eps), int(adam_step), _p(losses), _p(stats), _p(ws), ws_bytes,
         _stream(observations)), "ppo_mlp_update")
   return losses, stats
 

@@ -324,8 +324,11 @@ int derl_b200_gae_host(const void* rewards_host, int rewards_f64, const float* v
  *   losses_dev [nsteps] float32, stats_dev [nsteps * DERL_LOSS_STATS] float32 out
  *     (nsteps = nepochs * ceil(nsamples / minibatch); stats as in K3, [10] = gradient norm
  *     before clipping).
+ *   workspace_dev >= derl_b200_ppo_mlp_update_workspace_bytes(obs_dim, act_dim) (the Adam moments
+ *     in the kernel's padded layout while it runs; contents undefined before and after).
  * derl_b200_ppo_mlp_update_smem_bytes: dynamic shared memory the shape needs, 0 = unsupported. */
 size_t derl_b200_ppo_mlp_update_smem_bytes(int obs_dim, int act_dim);
+size_t derl_b200_ppo_mlp_update_workspace_bytes(int obs_dim, int act_dim);
 int derl_b200_ppo_mlp_update(
     float* const* params_dev, float* const* exp_avg_dev, float* const* exp_avg_sq_dev, int obs_dim,
     int act_dim, const void* observations_dev, int obs_f64, const float* actions_dev,
@@ -334,7 +337,7 @@ int derl_b200_ppo_mlp_update(
     int64_t minibatch, int normalize_advantages, double adv_epsilon, int has_clip, double cliprange,
     double value_loss_coef, double entropy_coef, double max_grad_norm, double lr, double beta1,
     double beta2, double adam_eps, int64_t adam_step, float* losses_dev, float* stats_dev,
-    void* stream);
+    void* workspace_dev, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
