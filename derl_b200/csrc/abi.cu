@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace derl {
 
@@ -99,6 +100,24 @@ int ensure_dynamic_smem(const void* func, int bytes) {
   if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   g_attrs.push_back(AttrKey{dev, func, bytes});
   return DERL_OK;
+}
+
+TmapEncodeFn tmap_encode_fn() {
+  static std::atomic<TmapEncodeFn> cached{nullptr};
+  TmapEncodeFn fn = cached.load(std::memory_order_acquire);
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<TmapEncodeFn>(p);
+      cached.store(fn, std::memory_order_release);
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return fn;
 }
 
 }  // namespace derl

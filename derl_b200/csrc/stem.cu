@@ -24,6 +24,7 @@
 // hi + lo) measured 1.48 ms per 32768 frames — exactly the legacy-MMA issue limit (one
 // m16n8k16 per 16 cycles per SM sub-partition); the int8 form halves the MMA count: 0.83 ms.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -274,6 +275,13 @@ int launch(const uint8_t* frames, const long long* rows, const float* weight, co
 }  // namespace
 }  // namespace derl
 
+namespace derl {
+bool stem_tc_available();
+int launch_stem_tc(const uint8_t* frames, const long long* rows, long long batch,
+                   long long frames_total, const float* weight, const float* bias, float* out,
+                   unsigned* mask_out, int out_block, cudaStream_t st);
+}  // namespace derl
+
 using namespace derl;
 
 extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, const int64_t* rows, int64_t batch,
@@ -289,6 +297,14 @@ extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, const int64_t* ro
   if (rc != DERL_OK) return rc;
   if (batch == 0) return DERL_OK;
   cudaStream_t st = as_stream(stream);
+  // float32 activations: the tcgen05 / tensor-memory kernel (stem_tc.cu; bit-identical results).
+  // DERL_STEM_MMA_SYNC=1 keeps the legacy mma.sync kernel (A/B measurements, tests).
+  const char* legacy = getenv("DERL_STEM_MMA_SYNC");
+  if (out_dtype == DERL_DTYPE_F32 && !(legacy && legacy[0] == '1') && stem_tc_available() &&
+      batch * 400 < (1ll << 31)) {
+    return launch_stem_tc(frames, reinterpret_cast<const long long*>(rows), batch, 0, weight, bias,
+                          reinterpret_cast<float*>(out), nullptr, out_block, st);
+  }
   return out_dtype == DERL_DTYPE_BF16
              ? launch<__nv_bfloat16>(frames, reinterpret_cast<const long long*>(rows), weight, bias,
                                      out, batch, out_block, st)

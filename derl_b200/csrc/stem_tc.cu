@@ -1,0 +1,342 @@
+// K6t — the NatureCNN stem forward (conv 8x8 / 4 over uint8 [84,84,4] frames + bias + ReLU,
+// derl/models.py:102-103,117-123) on the 5th-generation tensor cores: tcgen05.mma kind::i8 with
+// the accumulators in tensor memory.  Same arithmetic as the mma.sync kernel in stem.cu (raw
+// uint8 frame bytes x two signed 8-bit digit planes of the weights, exact int32 accumulation,
+// fp32 recombination), hence bit-identical results; what changes is who moves the operands.
+//
+// Operand formulation.  With the frame cut into 4x4-pixel blocks (space-to-depth(4): block
+// (Y, X) = rows 4Y..4Y+3, columns 4X..4X+3, 64 bytes) the 8x8/4 convolution is a 2x2/1
+// convolution over 21x21 blocks: for kernel quadrant (a, b) the output pixel (oy, ox) reads block
+// (oy + a, ox + b).  One TMA tensor copy lands the frame in shared memory with its 84 image rows
+// PERMUTED, row 4Y + i -> slot i * 21 + Y (tensor map {84 u32, 21 Y, 4 i, frames}, box = one
+// frame): plane i then holds, for every block m' = 21 Y + X, the 16 bytes (j, c) of its image row
+// i, as 16-byte units at address 16 m'.  That is exactly the canonical NO-SWIZZLE K-major UMMA
+// operand — core matrix = 8 consecutive blocks x 16 bytes = 128 contiguous bytes, next 8 blocks
+// at +128 B (SBO), the K-neighbour chunk (i + 1) at +7056 B (LBO) — and with pixels numbered
+// m = 21 oy + ox (one junk column per output row) quadrant (a, b) is the same operand started
+// 16 (21 a + b) bytes later.  No im2col, no byte transpose, no fragment loads: per frame the
+// tensor core reads the landed bytes in 32 instructions
+//     D[128 pixels x 64 (plane, channel)] += A[128 x 32 B] * W[64 x 32 B]
+// (4 pixel tiles x 4 quadrants x 2 K-halves; ~1 k tensor cycles) issued by one thread.
+// The 64 accumulator columns of a pixel (32 channels x 2 digit planes) sit in ONE tensor-memory
+// lane, so the epilogue thread that owns the pixel recombines the planes, applies scale, /255,
+// bias and ReLU and holds the pixel's 128 output bytes — written to a 128B-swizzled staging tile
+// (conflict-free) that a TMA tensor store drains as two 25.6 KB boxes per frame.
+//
+// Roles (384 threads, one persistent CTA per SM): warp 0 = TMA producer (frames, double
+// buffered), warp 1 = MMA issuer + TMEM owner, warps 4-7 / 8-11 = two epilogue groups taking
+// alternate frames (each owns one 256-column accumulator buffer and one staging tile), so that
+// frame f+1's loads and MMAs and frame f's epilogue and frame f-1's store overlap.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace derl {
+namespace {
+
+constexpr int kImgBytes = 84 * 84 * 4;        // 28224
+constexpr int kPlaneBytes = 21 * 336;         // 7056: one tap-row plane [21 Y][336 B]
+constexpr int kFrameBuf = 29824;              // frame + over-read slack of the last pixel tile
+constexpr int kOutC = 32, kPixPad = 420;      // padded pixel index m = 21 oy + ox, ox = 20 is junk
+constexpr int kMTiles = 4;                    // 4 x 128 rows
+constexpr int kWBytes = 16 * 64 * 16;         // [k16][n'][16 B]
+constexpr int kStageBytes = 400 * 128;        // one frame's fp32 activation
+constexpr int kThreads = 384;
+constexpr uint32_t kTmemCols = 512;
+
+struct TcSmem {   // byte offsets from a 1024-aligned base
+  static constexpr int stage = 0;                              // [2][51200]
+  static constexpr int frame = stage + 2 * kStageBytes;        // [2][29824]
+  static constexpr int w = frame + 2 * kFrameBuf;              // 16384
+  static constexpr int scale = w + kWBytes;                    // float[32]
+  static constexpr int bias = scale + 128;                     // float[32]
+  static constexpr int bars = bias + 128;                      // 8 mbarriers
+  static constexpr int slot = bars + 64;                       // tmem base address
+  static constexpr int bytes = slot + 16;
+  static constexpr int alloc = bytes + 1024;                   // slack for the manual alignment
+};
+static_assert(TcSmem::frame % 128 == 0 && TcSmem::w % 128 == 0, "smem alignment");
+static_assert(TcSmem::alloc <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t kIdesc = umma_idesc_i8(128, 64, /*a u8*/ 0, /*b s8*/ 1, 0, 0);
+
+__device__ __forceinline__ void tma_store_2d_f(const void* tmap, const void* smem_src, int c0,
+                                               int c1) {
+  tma_store_2d(tmap, smem_src, c0, c1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
+                         const __grid_constant__ CUtensorMap tm_out,
+                         const long long* __restrict__ rows, const float* __restrict__ weight,
+                         const float* __restrict__ bias, unsigned* __restrict__ mask_out,
+                         long long batch, int out_block) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* wsm = smem + TcSmem::w;
+  float* ssm = reinterpret_cast<float*>(smem + TcSmem::scale);
+  float* bsm = reinterpret_cast<float*>(smem + TcSmem::bias);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);   // TMA -> MMA
+  uint64_t* empty = full + 2;                                          // MMA -> TMA
+  uint64_t* tfull = full + 4;                                          // MMA -> epilogue
+  uint64_t* tempty = full + 6;                                         // epilogue -> MMA
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + TcSmem::slot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long first = blockIdx.x, stride = gridDim.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_frames);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 1) tmem_alloc(slot, kTmemCols);
+
+  // ---- per-channel scales and the two digit planes of the weights, [k16][n'][16 B]:
+  // k16 = (a * 2 + b) * 4 + i, n' = plane * 32 + channel, byte j * 4 + c  <->  W[n][c][4a+i][4b+j]
+  for (int n = warp; n < kOutC; n += kThreads / 32) {
+    float m = 0.f;
+    for (int k = lane; k < 256; k += 32) m = fmaxf(m, fabsf(__ldg(weight + n * 256 + k)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) ssm[n] = m > 0.f ? m / 127.f : 1.f;
+  }
+  if (tid < kOutC) bsm[tid] = __ldg(bias + tid);
+  __syncthreads();
+  for (int e = tid; e < 16 * kOutC; e += kThreads) {
+    const int n = e & 31, k16 = e >> 5;
+    const int q = k16 >> 2, i = k16 & 3, kh = 4 * (q >> 1) + i, kw0 = 4 * (q & 1);
+    const float s = ssm[n], inv = 1.f / s;
+    unsigned p1[4], p2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p1[j] = 0u;
+      p2[j] = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float w = __ldg(weight + ((n * 4 + c) * 8 + kh) * 8 + kw0 + j);
+        const float q1 = rintf(w * inv);
+        const float q2 = fminf(fmaxf(rintf((w - q1 * s) * 254.f * inv), -127.f), 127.f);
+        p1[j] |= ((unsigned)(int)q1 & 0xffu) << (8 * c);
+        p2[j] |= ((unsigned)(int)q2 & 0xffu) << (8 * c);
+      }
+    }
+    *reinterpret_cast<uint4*>(wsm + k16 * 1024 + n * 16) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(wsm + k16 * 1024 + (32 + n) * 16) =
+        make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  }
+  fence_proxy_async_smem();     // generic-proxy writes of W -> visible to the tensor core
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (long long f = first; f < batch; f += stride, ++it) {
+        const int b = it & 1;
+        mbar_wait(&empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(&full[b], kImgBytes);
+        const long long src = rows ? __ldg(rows + f) : f;   // fused minibatch gather
+        tma_load_4d(smem + TcSmem::frame + b * kFrameBuf, &tm_frames, 0, 0, 0, (int)src, &full[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t w_addr = smem_u32(wsm);
+      int it = 0;
+      for (long long f = first; f < batch; f += stride, ++it) {
+        const int b = it & 1, g = it & 1;
+        const unsigned ph = (unsigned)((it >> 1) & 1);
+        mbar_wait(&tempty[g], ph ^ 1u);     // the epilogue has drained this accumulator buffer
+        mbar_wait(&full[b], ph);            // the frame has landed
+        tcgen05_fence_after();
+        const uint32_t f_addr = smem_u32(smem + TcSmem::frame + b * kFrameBuf);
+#pragma unroll 1
+        for (int mt = 0; mt < kMTiles; ++mt) {
+          const uint32_t d = tmem + (uint32_t)(g * 256 + mt * 64);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int ip = 0; ip < 2; ++ip) {
+              const uint32_t a_addr = f_addr + (uint32_t)(2 * ip * kPlaneBytes +
+                                                         (21 * (q >> 1) + (q & 1)) * 16 + mt * 2048);
+              const uint32_t b_addr = w_addr + (uint32_t)((q * 4 + 2 * ip) * 1024);
+              umma_i8(d, umma_desc(a_addr, kPlaneBytes, 128), umma_desc(b_addr, 1024, 128), kIdesc,
+                      (q | ip) != 0);
+            }
+          }
+        }
+        umma_commit(&empty[b]);    // frame buffer may be refilled once these MMAs have read it
+        umma_commit(&tfull[g]);    // accumulators complete
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue groups
+    const int g = (warp - 4) >> 2;            // group 0: warps 4-7, group 1: warps 8-11
+    const int wq = warp & 3;                  // tensor-memory lane quarter of this warp
+    const int gt = tid - (4 + 4 * g) * 32;    // thread index inside the group
+    uint8_t* stage = smem + TcSmem::stage + g * kStageBytes;
+    const float inv255 = 1.0f / 255.0f, inv254 = 1.0f / 254.0f;
+    int it = 0, mine = 0;
+    for (long long f = first; f < batch; f += stride, ++it) {
+      if ((it & 1) != g) continue;
+      const unsigned ph = (unsigned)((it >> 1) & 1);
+      // the previous store of this staging tile must have finished READING it
+      if (gt == 0 && mine > 0) bulk_wait_read<0>();
+      named_bar_sync(1 + g, 128);
+      mbar_wait(&tfull[g], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < kMTiles; ++mt) {
+        const int m = mt * 128 + wq * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 256 + mt * 64);
+        uint32_t v1[32], v2[32];
+        tmem_ld_32x32(taddr, v1);
+        tmem_ld_32x32(taddr + 32, v2);
+        tmem_ld_wait();
+        const int oy = m / 21, ox = m - oy * 21;
+        const bool valid = m < kPixPad && ox < 20;
+        int row = oy * 20 + ox;
+        const int pixel = row;
+        if (out_block == 2) row = (((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
+        unsigned bits = 0u;
+        uint8_t* dst = stage + row * 128;
+        const int sw = row & 7;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float y[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int ch = c4 * 4 + k;
+            const float sc = ssm[ch] * inv255;
+            float x = ((float)(int)v1[ch] + (float)(int)v2[ch] * inv254) * sc + bsm[ch];
+            x = fmaxf(x, 0.f);
+            bits |= (x > 0.f ? 1u : 0u) << ch;
+            y[k] = x;
+          }
+          if (valid) {
+            *reinterpret_cast<float4*>(dst + ((c4 ^ sw) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+        if (valid && mask_out != nullptr) mask_out[f * 400 + pixel] = bits;
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty[g]);               // accumulator buffer g may be overwritten
+      fence_proxy_async_smem();              // staging writes -> visible to the TMA store
+      named_bar_sync(1 + g, 128);
+      if (gt == 0) {
+        tma_store_2d_f(&tm_out, stage, 0, (int)(f * 400));
+        tma_store_2d_f(&tm_out, stage + 200 * 128, 0, (int)(f * 400 + 200));
+        bulk_commit();
+      }
+      ++mine;
+    }
+    if (gt == 0) bulk_wait<0>();             // stores complete before the CTA retires its smem
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ tensor maps (memoised per thread)
+struct MapKey {
+  const void* base;
+  long long n;
+  int kind;
+  bool operator==(const MapKey& o) const { return base == o.base && n == o.n && kind == o.kind; }
+};
+constexpr int kMapSlots = 16;
+struct MapCache {
+  MapKey keys[kMapSlots];
+  CUtensorMap maps[kMapSlots];
+  int used = 0, next = 0;
+};
+
+bool cached_map(CUtensorMap* out, const MapKey& key, bool (*make)(CUtensorMap*, const MapKey&)) {
+  static thread_local MapCache cache;
+  for (int i = 0; i < cache.used; ++i) {
+    if (cache.keys[i] == key) {
+      *out = cache.maps[i];
+      return true;
+    }
+  }
+  if (!make(out, key)) return false;
+  const int s = cache.used < kMapSlots ? cache.used++ : cache.next;
+  cache.next = (s + 1) % kMapSlots;
+  cache.keys[s] = key;
+  cache.maps[s] = *out;
+  return true;
+}
+
+// frames [n][84 rows][336 B] seen as {84 u32 (one image row), 21 Y (stride 4 rows), 4 i (stride
+// 1 row), n frames}; box = one frame -> shared memory [i][Y][336 B].
+bool make_frames_map(CUtensorMap* map, const MapKey& key) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[4] = {84, 21, 4, (cuuint64_t)key.n};
+  cuuint64_t strides[3] = {4 * 336, 336, (cuuint64_t)kImgBytes};
+  cuuint32_t box[4] = {84, 21, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(key.base), dims, strides,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// out [n * 400 rows][32 f32]; box = 200 rows, 128B swizzle (the staging tile's layout).
+bool make_out_map(CUtensorMap* map, const MapKey& key) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {32, (cuuint64_t)key.n * 400};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {32, 200};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(key.base), dims, strides,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool stem_tc_available() { return tmap_encode_fn() != nullptr; }
+
+// frames_total: rows of the frames array (>= batch; the gather source when rows != NULL, where
+// the caller may not know it: pass 0 and the map is built for 2^30 frames — the indices are
+// trusted, as in every gather of this library).
+int launch_stem_tc(const uint8_t* frames, const long long* rows, long long batch,
+                   long long frames_total, const float* weight, const float* bias, float* out,
+                   unsigned* mask_out, int out_block, cudaStream_t st) {
+  if (frames_total <= 0) frames_total = rows ? (1ll << 30) : batch;
+  CUtensorMap tm_frames, tm_out;
+  if (!cached_map(&tm_frames, MapKey{frames, frames_total, 0}, make_frames_map) ||
+      !cached_map(&tm_out, MapKey{out, batch, 1}, make_out_map)) {
+    set_error("stem_conv_relu: cuTensorMapEncodeTiled failed (batch %lld)", batch);
+    return DERL_E_CUDA;
+  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(stem_conv_relu_tc_kernel),
+                                   TcSmem::alloc))
+    return rc;
+  long long grid = sm_count();
+  if (grid > batch) grid = batch;
+  stem_conv_relu_tc_kernel<<<(unsigned)grid, kThreads, TcSmem::alloc, st>>>(
+      tm_frames, tm_out, rows, weight, bias, mask_out, batch, out_block);
+  DERL_LAUNCH_CHECK("stem_conv_relu_tc_kernel");
+  return DERL_OK;
+}
+
+}  // namespace derl

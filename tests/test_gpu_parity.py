@@ -1349,3 +1349,51 @@ def test_fused_mlp_plan_rejects_what_it_does_not_model():
   assert FusedMLPUpdate.plan(alg) is None
   assert _lib.load().derl_b200_ppo_mlp_update_smem_bytes(376, 17) == 0   # Humanoid: too wide
   assert _lib.load().derl_b200_ppo_mlp_update_smem_bytes(17, 6) > 0
+
+
+# =============================================================================== K6t: tcgen05 stem
+@pytest.mark.parametrize("batch", [1, 3, 149, 700])
+@pytest.mark.parametrize("out_block", [1, 2])
+def test_stem_tcgen05_kernel_is_bit_identical_to_the_mma_sync_kernel(monkeypatch, batch, out_block):
+  """K6t (csrc/stem_tc.cu: tcgen05.mma kind::i8, accumulators in tensor memory, TMA-permuted
+  frame tile as a no-swizzle K-major operand) computes the same exact int32 sums and the same
+  fp32 epilogue as the legacy mma.sync kernel, so the two must agree bit for bit — with and
+  without the fused gather (`rows`, repeated indices included) — and both stay within 1e-4 of
+  the activation scale of the float32 convolution (derl/models.py:102-103,117-123)."""
+  gen = torch.Generator(device=DEV).manual_seed(batch)
+  weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.1
+  bias = torch.randn(32, device=DEV, generator=gen) * 0.1
+  frames = torch.randint(0, 256, (batch, 84, 84, 4), dtype=torch.uint8, device=DEV, generator=gen)
+  rows = torch.randint(0, batch, (batch + 3,), device=DEV, generator=gen)
+  for sel in (None, rows):
+    monkeypatch.delenv("DERL_STEM_MMA_SYNC", raising=False)
+    new = K.stem_conv_relu(frames, weight, bias, torch.float32, out_block, sel)
+    monkeypatch.setenv("DERL_STEM_MMA_SYNC", "1")
+    old = K.stem_conv_relu(frames, weight, bias, torch.float32, out_block, sel)
+    assert torch.equal(new, old), f"rows={'yes' if sel is not None else 'no'}"
+  monkeypatch.delenv("DERL_STEM_MMA_SYNC", raising=False)
+  if out_block == 1:
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+      src = frames.permute(0, 3, 1, 2).float() / 255
+      want = torch.relu(torch.nn.functional.conv2d(src, weight, bias, stride=4)).permute(0, 2, 3, 1)
+    finally:
+      torch.backends.cudnn.allow_tf32 = True
+    got = K.stem_conv_relu(frames, weight, bias, torch.float32, 1, None)
+    assert (got - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
+def test_stem_tcgen05_kernel_is_deterministic_under_repetition():
+  """Stress for the mbarrier rings of K6t (TMA -> MMA -> two epilogue groups -> TMA store): 30
+  launches over batch sizes that leave CTAs with 0, 1 or many frames must all give the first
+  launch's bytes (a race in the pipeline shows up as a sporadic difference)."""
+  gen = torch.Generator(device=DEV).manual_seed(9)
+  weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.1
+  bias = torch.randn(32, device=DEV, generator=gen) * 0.1
+  for batch in (5, 148, 151, 2000):
+    frames = torch.randint(0, 256, (batch, 84, 84, 4), dtype=torch.uint8, device=DEV,
+                           generator=gen)
+    ref = K.stem_conv_relu(frames, weight, bias, torch.float32, 2, None)
+    for _ in range(30):
+      again = K.stem_conv_relu(frames, weight, bias, torch.float32, 2, None)
+      assert torch.equal(again, ref)
