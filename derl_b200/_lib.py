@@ -61,6 +61,9 @@ SIGNATURES = {
                                         _ptr, _ptr, _i64, _ptr, _i64, _i64, _int, _f64, _int, _f64,
                                         _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _ptr, _ptr,
                                         _ptr, _size, _ptr]),
+    "derl_b200_stem_conv_relu_mask": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _int, _ptr]),
+    "derl_b200_stem_backward_masked": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _int, _ptr, _ptr, _ptr,
+                                              _size, _ptr]),
     "derl_b200_gae_host": (_int, [_ptr, _int, _ptr, _ptr, _ptr, _i64, _i64, _f64, _f64, _int,
                                   _f64, _ptr, _ptr, _ptr]),
 }

@@ -311,3 +311,22 @@ extern "C" int derl_b200_stem_conv_relu(const uint8_t* frames, const int64_t* ro
              : launch<float>(frames, reinterpret_cast<const long long*>(rows), weight, bias, out,
                              batch, out_block, st);
 }
+
+extern "C" int derl_b200_stem_conv_relu_mask(const uint8_t* frames, const int64_t* rows,
+                                             int64_t batch, const float* weight, const float* bias,
+                                             float* out, uint32_t* relu_mask, int out_block,
+                                             void* stream) {
+  DERL_REQUIRE(out_block == 1 || out_block == 2, "stem_conv_relu_mask: out_block must be 1 or 2");
+  DERL_REQUIRE(frames && weight && bias && out && relu_mask && batch >= 0,
+               "stem_conv_relu_mask: bad arguments");
+  DERL_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)out & 127) == 0 &&
+                   ((uintptr_t)relu_mask & 15) == 0,
+               "stem_conv_relu_mask: frames / mask must be 16-byte, out 128-byte aligned");
+  DERL_REQUIRE(batch * 400 < (1ll << 31), "stem_conv_relu_mask: batch too large");
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  if (batch == 0) return DERL_OK;
+  DERL_REQUIRE(stem_tc_available(), "stem_conv_relu_mask: cuTensorMapEncodeTiled is unavailable");
+  return launch_stem_tc(frames, reinterpret_cast<const long long*>(rows), batch, 0, weight, bias,
+                        out, relu_mask, out_block, as_stream(stream));
+}

@@ -416,6 +416,19 @@ stem_bwd_reduce_kernel(const float* __restrict__ partial_w, const float* __restr
 }
 
 }  // namespace
+
+int launch_stem_bwd_reduce(const float* partial_w, const float* partial_b, int ctas, float* grad_w,
+                           float* grad_b, cudaStream_t st) {
+  stem_bwd_reduce_kernel<<<kPartial / 32 + 1, 256, 0, st>>>(partial_w, partial_b, ctas, grad_w,
+                                                           grad_b);
+  DERL_LAUNCH_CHECK("stem_bwd_reduce_kernel");
+  return DERL_OK;
+}
+
+bool stem_tc_available();
+int launch_stem_bwd_tc(const uint8_t* frames, const long long* rows, long long batch,
+                       const float* grad_out, const unsigned* mask, int blocked, float* grad_w,
+                       float* grad_b, void* workspace, cudaStream_t st);
 }  // namespace derl
 
 using namespace derl;
@@ -450,8 +463,28 @@ extern "C" int derl_b200_stem_backward(const uint8_t* frames, const int64_t* row
       frames, reinterpret_cast<const long long*>(rows), grad_out, out, partial_w, partial_b, batch,
       blocked);
   DERL_LAUNCH_CHECK("stem_bwd_kernel");
-  stem_bwd_reduce_kernel<<<kPartial / 32 + 1, 256, 0, st>>>(partial_w, partial_b, (int)grid,
-                                                                  grad_weight, grad_bias);
-  DERL_LAUNCH_CHECK("stem_bwd_reduce_kernel");
-  return DERL_OK;
+  return launch_stem_bwd_reduce(partial_w, partial_b, (int)grid, grad_weight, grad_bias, st);
+}
+
+extern "C" int derl_b200_stem_backward_masked(const uint8_t* frames, const int64_t* rows,
+                                              int64_t batch, const float* grad_out,
+                                              const uint32_t* relu_mask, int blocked,
+                                              float* grad_weight, float* grad_bias,
+                                              void* workspace, size_t workspace_bytes,
+                                              void* stream) {
+  DERL_REQUIRE(frames && grad_out && relu_mask && grad_weight && grad_bias && workspace &&
+                   batch >= 1, "stem_backward_masked: bad arguments");
+  DERL_REQUIRE(blocked == 0 || blocked == 1, "stem_backward_masked: blocked must be 0 or 1");
+  DERL_REQUIRE((((uintptr_t)frames | (uintptr_t)grad_out | (uintptr_t)relu_mask) & 15) == 0,
+               "stem_backward_masked: inputs must be 16-byte aligned");
+  int rc = require_device();
+  if (rc != DERL_OK) return rc;
+  if (workspace_bytes < derl_b200_stem_backward_workspace_bytes()) {
+    set_error("stem_backward_masked: workspace %zu B too small", workspace_bytes);
+    return DERL_E_WORKSPACE;
+  }
+  DERL_REQUIRE(stem_tc_available(), "stem_backward_masked: cuTensorMapEncodeTiled is unavailable");
+  return launch_stem_bwd_tc(frames, reinterpret_cast<const long long*>(rows), batch, grad_out,
+                            relu_mask, blocked, grad_weight, grad_bias, workspace,
+                            as_stream(stream));
 }

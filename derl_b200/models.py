@@ -108,22 +108,36 @@ class _StemConvReLU(torch.autograd.Function):
   mapped back to [32, 4, 8, 8].  With `rows` both kernels read frames[rows] in place: the
   minibatch gather fused into the layer (runners/row_selection.py)."""
 
+  tensor_memory = True    # float32 activations: the tcgen05 pair K6t / K7t (ReLU mask as bits)
+
   @staticmethod
   def forward(ctx, frames, weight, bias, dtype, out_block, rows=None):
     """rows: int64 indices — the batch is frames[rows], read in place (fused minibatch gather)."""
-    out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype, out_block,
-                                             rows)
+    mask = None
+    if _StemConvReLU.tensor_memory and dtype == torch.float32 and _StemConvReLU.fused_backward:
+      out, mask = torch.ops.derl_b200.stem_conv_relu_mask(frames, weight.contiguous(), bias,
+                                                          out_block, rows)
+    else:
+      out = torch.ops.derl_b200.stem_conv_relu(frames, weight.contiguous(), bias, dtype,
+                                               out_block, rows)
     out = out.permute(0, 3, 1, 2)   # channels-last storage seen as NCHW
-    ctx.save_for_backward(frames, out, rows)
+    # with the mask the backward never reads the activation (its consumer, the next layer, keeps
+    # it alive anyway); without it the activation itself is the mask
+    ctx.save_for_backward(frames, out if mask is None else mask, rows)
+    ctx.has_mask = mask is not None
     ctx.weight_dtype, ctx.out_block = weight.dtype, out_block
     return out
 
-  fused_backward = True   # K7: mask + bias grad + weight grad in one INT8 tensor-core kernel
+  fused_backward = True   # K7 / K7t: mask + bias grad + weight grad in one INT8 tensor-core kernel
 
   @staticmethod
   def backward(ctx, grad_out):
     frames, out, rows = ctx.saved_tensors
     grad_out = grad_out.contiguous(memory_format=torch.channels_last)
+    if ctx.has_mask:
+      grad_w, grad_b = torch.ops.derl_b200.stem_backward_masked(frames, grad_out, out,
+                                                                ctx.out_block == 2, rows)
+      return None, grad_w.to(ctx.weight_dtype), grad_b, None, None, None
     if _StemConvReLU.fused_backward and out.dtype == torch.float32:
       grad_w, grad_b = torch.ops.derl_b200.stem_backward(frames, grad_out, out,
                                                          ctx.out_block == 2, rows)

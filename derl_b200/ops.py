@@ -416,6 +416,73 @@ def _(frames, grad_out, out, blocked, rows=None):
       frames.new_empty(32, dtype=torch.float32)
 
 
+@torch.library.custom_op("derl_b200::stem_conv_relu_mask", mutates_args=(), device_types="cuda")
+def stem_conv_relu_mask(frames: Tensor, weight: Tensor, bias: Tensor, out_block: int = 1,
+                        rows: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+  """K6t (tcgen05 + tensor memory): float32 `stem_conv_relu` that also returns the ReLU mask,
+  uint32 [B, 400] with bit c of word (oy * 20 + ox) = (activation of channel c > 0) — what
+  `stem_backward_masked` reads instead of the 32x larger float32 activation."""
+  _dense(frames, "frames", (torch.uint8,))
+  batch = _check_rows(frames, rows)
+  _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
+  _dense(weight, "weight", (torch.float32,))
+  _dense(bias, "bias", (torch.float32,))
+  _need(tuple(weight.shape) == (32, 4, 8, 8) and tuple(bias.shape) == (32,),
+        "stem_conv_relu_mask is specialised to weight [32,4,8,8], bias [32]")
+  _need(out_block in (1, 2), "out_block must be 1 or 2")
+  shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
+  out = torch.empty(shape, dtype=torch.float32, device=frames.device)
+  mask = torch.empty((batch, 400), dtype=torch.int32, device=frames.device)
+  with _device_of(frames, "stem_conv_relu"):
+    _lib.check(_lib.load().derl_b200_stem_conv_relu_mask(
+        _p(frames), _p(rows) if rows is not None else None, batch, _p(weight), _p(bias), _p(out),
+        _p(mask), out_block, _stream(frames)), "stem_conv_relu_mask")
+  return out, mask
+
+
+@stem_conv_relu_mask.register_fake
+def _(frames, weight, bias, out_block=1, rows=None):
+  batch = frames.shape[0] if rows is None else rows.shape[0]
+  shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
+  return (frames.new_empty(shape, dtype=torch.float32),
+          frames.new_empty((batch, 400), dtype=torch.int32))
+
+
+@torch.library.custom_op("derl_b200::stem_backward_masked", mutates_args=(), device_types="cuda")
+def stem_backward_masked(frames: Tensor, grad_out: Tensor, mask: Tensor, blocked: bool,
+                         rows: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+  """K7t (tcgen05 + tensor memory): (grad_weight [32,4,8,8], grad_bias [32]) of the stem from the
+  uint8 frames, the gradient w.r.t. its output (channels-last [B,32,20,20], or [B,128,10,10]
+  when `blocked`) and the ReLU mask `stem_conv_relu_mask` returned."""
+  _dense(frames, "frames", (torch.uint8,))
+  _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
+  batch = _check_rows(frames, rows)
+  _need(batch >= 1, "stem_backward_masked needs at least one frame")
+  want = (batch, 128, 10, 10) if blocked else (batch, 32, 20, 20)
+  _need(grad_out.dtype == torch.float32 and tuple(grad_out.shape) == want
+        and grad_out.is_contiguous(memory_format=torch.channels_last),
+        f"grad_out must be a channels_last float32 tensor of shape {want}")
+  _dense(mask, "mask", (torch.int32,))
+  _need(tuple(mask.shape) == (batch, 400), f"mask must be int32 [{batch}, 400]")
+  grad_w = torch.empty((32, 4, 8, 8), dtype=torch.float32, device=frames.device)
+  grad_b = torch.empty(32, dtype=torch.float32, device=frames.device)
+  lib = _lib.load()
+  ws_bytes = lib.derl_b200_stem_backward_workspace_bytes()
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+  with _device_of(frames, "stem_backward"):
+    _lib.check(lib.derl_b200_stem_backward_masked(
+        _p(frames), _p(rows) if rows is not None else None, batch, _p(grad_out), _p(mask),
+        int(blocked), _p(grad_w), _p(grad_b), _p(ws), ws_bytes, _stream(frames)),
+        "stem_backward_masked")
+  return grad_w, grad_b
+
+
+@stem_backward_masked.register_fake
+def _(frames, grad_out, mask, blocked, rows=None):
+  return frames.new_empty((32, 4, 8, 8), dtype=torch.float32), \
+      frames.new_empty(32, dtype=torch.float32)
+
+
 # --------------------------------------------------------------------------- K5: ReLU bwd
 @torch.library.custom_op("derl_b200::relu_bwd_bias", mutates_args=(), device_types="cuda")
 def relu_bwd_bias(grad_out: Tensor, out: Tensor, unblock: int = 1) -> Tuple[Tensor, Tensor]:

@@ -29,7 +29,8 @@ extern "C" {
 #endif
 
 /* 2: derl_b200_stem_conv_relu / derl_b200_stem_backward gained `rows_dev` (fused minibatch gather).
- * 3: derl_b200_ppo_mlp_update (whole PPO update of the MuJoCo-shaped actor-critic in one launch). */
+ * 3: derl_b200_ppo_mlp_update (whole PPO update of the MuJoCo-shaped actor-critic in one launch),
+ *    derl_b200_stem_conv_relu_mask / derl_b200_stem_backward_masked (tcgen05 stem pair). */
 #define DERL_B200_ABI_VERSION 3
 
 enum {
@@ -300,6 +301,25 @@ int derl_b200_gae_host(const void* rewards_host, int rewards_f64, const float* v
                        const uint8_t* resets_host, const float* last_value_host, int64_t T,
                        int64_t N, double gamma, double lambda, int normalize, double epsilon,
                        float* advantages_host, float* value_targets_host, void* stream);
+
+/* ------------------------------------------------------------------ K6t / K7t: the stem on tcgen05 + tensor memory
+ * derl_b200_stem_conv_relu itself runs the tcgen05 kernel for float32 outputs (the mma.sync
+ * kernel remains for bf16 outputs and under DERL_STEM_MMA_SYNC=1; results are bit-identical).
+ * The two entry points below are the pair a training step uses: the forward additionally emits
+ * the ReLU mask as one bit per activation, and the backward consumes that mask instead of
+ * re-reading the float32 activation (51 200 B per frame less HBM traffic).
+ *   relu_mask [batch, 400] uint32: bit c of word (oy * 20 + ox) = (out[pixel, channel c] > 0),
+ *     pixels in plain order whatever out_block / blocked says.
+ *   out must be 128-byte aligned (TMA store); everything else as in derl_b200_stem_conv_relu /
+ *   derl_b200_stem_backward (derl/models.py:102-103,117-123 forward; its autograd backward). */
+int derl_b200_stem_conv_relu_mask(const uint8_t* frames_dev, const int64_t* rows_dev, int64_t batch,
+                                  const float* weight_dev, const float* bias_dev, float* out_dev,
+                                  uint32_t* relu_mask_dev, int out_block, void* stream);
+int derl_b200_stem_backward_masked(const uint8_t* frames_dev, const int64_t* rows_dev,
+                                   int64_t batch, const float* grad_out_dev,
+                                   const uint32_t* relu_mask_dev, int blocked,
+                                   float* grad_weight_dev, float* grad_bias_dev,
+                                   void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ K8: whole PPO update, MLP actor-critic
  * One launch = every epoch and minibatch of one rollout's PPO update for the reference's

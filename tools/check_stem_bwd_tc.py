@@ -1,0 +1,104 @@
+"""Hardware check of the tcgen05 stem backward (K7t) and of the ReLU mask K6t emits, against
+float32 autograd (tolerances of tests/test_gpu_parity.py) and the legacy mma.sync kernel K7."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import derl_b200  # noqa: E402,F401
+
+K = torch.ops.derl_b200
+
+
+def s2d2(x):   # [B,20,20,32] -> [B,10,10,128]
+  return K.space_to_depth(x.contiguous(), 2, False)
+
+
+def main():
+  gen = torch.Generator(device="cuda").manual_seed(1)
+  weight = (torch.randn(32, 4, 8, 8, device="cuda", generator=gen) * 0.1).requires_grad_()
+  bias = (torch.randn(32, device="cuda", generator=gen) * 0.1).requires_grad_()
+  torch.backends.cudnn.allow_tf32 = False
+  ok = True
+  for batch in (1, 2, 5, 148, 149, 600):
+    frames = torch.randint(0, 256, (batch, 84, 84, 4), dtype=torch.uint8, device="cuda",
+                           generator=gen)
+    out, mask = K.stem_conv_relu_mask(frames, weight.detach(), bias.detach(), 1, None)
+    torch.cuda.synchronize()
+    want_mask = ((out > 0).to(torch.int64) << torch.arange(32, device="cuda")).sum(-1).reshape(batch, 400)
+    got_mask = mask.to(torch.int64) & 0xffffffff
+    mask_ok = torch.equal(got_mask, want_mask)
+    grad = torch.randn(batch, 20, 20, 32, device="cuda", generator=gen)
+    grad[batch // 2] *= 1e-3    # a frame with small gradients: block floating point is per frame
+    # float32 reference with the same mask
+    src = frames.permute(0, 3, 1, 2).float() / 255
+    pre = torch.nn.functional.conv2d(src, weight, bias, stride=4)
+    act = torch.relu(pre)
+    gw, gb = torch.autograd.grad(act, (weight, bias), grad.permute(0, 3, 1, 2))
+    for blocked in (False, True):
+      g_in = (s2d2(grad) if blocked else grad).permute(0, 3, 1, 2)
+      o_in = (s2d2(out) if blocked else out).permute(0, 3, 1, 2)
+      t0 = time.time()
+      nw, nb = K.stem_backward_masked(frames, g_in, mask, blocked, None)
+      torch.cuda.synchronize()
+      ow, ob = K.stem_backward(frames, g_in, o_in, blocked, None)
+      torch.cuda.synchronize()
+      ew = (nw - gw).abs().max().item() / gw.abs().max().item()
+      eb = (nb - gb).abs().max().item() / gb.abs().max().item()
+      ew_old = (ow - gw).abs().max().item() / gw.abs().max().item()
+      dn = (nw - ow).abs().max().item() / gw.abs().max().item()
+      good = ew < 2e-4 and eb < 1e-5
+      ok = ok and good and mask_ok
+      print(f"batch {batch} blocked {int(blocked)}: mask {mask_ok}  dW err {ew:.2e} (K7 {ew_old:.2e}, "
+            f"K7t-K7 {dn:.2e})  db err {eb:.2e}  {'ok' if good else 'BAD'} ({time.time() - t0:.2f}s)",
+            flush=True)
+    rows = torch.randint(0, batch, (batch + 3,), device="cuda", generator=gen)
+    out_r, mask_r = K.stem_conv_relu_mask(frames, weight.detach(), bias.detach(), 2, rows)
+    grad_r = torch.randn(batch + 3, 128, 10, 10, device="cuda", generator=gen).contiguous(
+        memory_format=torch.channels_last)
+    a = K.stem_backward_masked(frames, grad_r, mask_r, True, rows)
+    b = K.stem_backward_masked(frames[rows].contiguous(), grad_r, mask_r, True, None)
+    same = torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    again = K.stem_backward_masked(frames, grad_r, mask_r, True, rows)
+    det = torch.equal(a[0], again[0])
+    ok = ok and same and det
+    print(f"batch {batch}: rows == materialised gather {same}, deterministic {det}", flush=True)
+  # timing
+  nb_ = 32768
+  frames = torch.randint(0, 256, (nb_, 84, 84, 4), dtype=torch.uint8, device="cuda", generator=gen)
+  out, mask = K.stem_conv_relu_mask(frames, weight.detach(), bias.detach(), 2, None)
+  g_in = torch.randn(nb_, 128, 10, 10, device="cuda", generator=gen).contiguous(
+      memory_format=torch.channels_last)
+  o_in = out.permute(0, 3, 1, 2)
+  for name, fn, nbytes in (
+      ("K7t tcgen05 (mask)", lambda: K.stem_backward_masked(frames, g_in, mask, True, None),
+       28224 + 51200 + 1600),
+      ("K7 mma.sync (fp32 act)", lambda: K.stem_backward(frames, g_in, o_in, True, None),
+       28224 + 2 * 51200)):
+    fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5):
+      fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 5
+    print(f"{name}: {ms:.3f} ms per {nb_} frames, {nb_ * nbytes / ms / 1e6:.0f} GB/s of its own "
+          f"algorithmic bytes", flush=True)
+  s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  s.record()
+  for _ in range(5):
+    K.stem_conv_relu_mask(frames, weight.detach(), bias.detach(), 2, None)
+  e.record()
+  torch.cuda.synchronize()
+  ms = s.elapsed_time(e) / 5
+  print(f"K6t with mask: {ms:.3f} ms per {nb_} frames, {nb_ * (28224 + 51200 + 1600) / ms / 1e6:.0f} GB/s",
+        flush=True)
+  print("OK" if ok else "MISMATCH", flush=True)
+  return 0 if ok else 1
+
+
+if __name__ == "__main__":
+  sys.exit(main())
