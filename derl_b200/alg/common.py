@@ -96,15 +96,21 @@ class Trainer:
     nrows = data["observations"].shape[0] if "observations" in data else 0
     # a flat gradient buffer (grad_sync) must keep its views alive: zero in place then
     keep_buffers = self.grad_sync is not None
+    arm = getattr(self.grad_sync, "arm", None)   # overlapped all-reduce: see derl_b200.parallel
     if not self.micro_batch or nrows <= self.micro_batch:
       loss = alg.loss(data)
       self.optimizer.zero_grad(set_to_none=not keep_buffers)
+      if arm is not None:
+        arm()
       loss.backward()
       return loss
     self.optimizer.zero_grad(set_to_none=not keep_buffers)
     total = None
-    for chunk, weight in _split_rows(data, self.micro_batch):
+    chunks = list(_split_rows(data, self.micro_batch))
+    for i, (chunk, weight) in enumerate(chunks):
       part = alg.loss(chunk) * weight
+      if arm is not None and i == len(chunks) - 1:
+        arm()                                    # this backward completes the gradients
       part.backward()
       total = part.detach() if total is None else total + part.detach()
     return total

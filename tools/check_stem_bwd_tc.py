@@ -16,7 +16,25 @@ def s2d2(x):   # [B,20,20,32] -> [B,10,10,128]
   return K.space_to_depth(x.contiguous(), 2, False)
 
 
+def profile_only():
+  """A short run for ncu: K6t (with mask) and K7t on 8192 frames."""
+  gen = torch.Generator(device="cuda").manual_seed(1)
+  weight = torch.randn(32, 4, 8, 8, device="cuda", generator=gen) * 0.1
+  bias = torch.randn(32, device="cuda", generator=gen) * 0.1
+  frames = torch.randint(0, 256, (8192, 84, 84, 4), dtype=torch.uint8, device="cuda", generator=gen)
+  g_in = torch.randn(8192, 128, 10, 10, device="cuda", generator=gen).contiguous(
+      memory_format=torch.channels_last)
+  for _ in range(3):
+    out, mask = K.stem_conv_relu_mask(frames, weight, bias, 2, None)
+    K.stem_conv_relu(frames, weight, bias, torch.float32, 2, None)
+    K.stem_backward_masked(frames, g_in, mask, True, None)
+  torch.cuda.synchronize()
+  return 0
+
+
 def main():
+  if "--profile" in sys.argv:
+    return profile_only()
   gen = torch.Generator(device="cuda").manual_seed(1)
   weight = (torch.randn(32, 4, 8, 8, device="cuda", generator=gen) * 0.1).requires_grad_()
   bias = (torch.randn(32, device="cuda", generator=gen) * 0.1).requires_grad_()
@@ -32,11 +50,12 @@ def main():
     mask_ok = torch.equal(got_mask, want_mask)
     grad = torch.randn(batch, 20, 20, 32, device="cuda", generator=gen)
     grad[batch // 2] *= 1e-3    # a frame with small gradients: block floating point is per frame
-    # float32 reference with the same mask
+    # float32 reference with the SAME ReLU mask (the kernels' own: a sign flip of a near-zero
+    # pre-activation between the int8 path and cuDNN is not what is being measured here)
     src = frames.permute(0, 3, 1, 2).float() / 255
     pre = torch.nn.functional.conv2d(src, weight, bias, stride=4)
-    act = torch.relu(pre)
-    gw, gb = torch.autograd.grad(act, (weight, bias), grad.permute(0, 3, 1, 2))
+    keep = (out > 0).permute(0, 3, 1, 2).float()
+    gw, gb = torch.autograd.grad(pre, (weight, bias), grad.permute(0, 3, 1, 2) * keep)
     for blocked in (False, True):
       g_in = (s2d2(grad) if blocked else grad).permute(0, 3, 1, 2)
       o_in = (s2d2(out) if blocked else out).permute(0, 3, 1, 2)
