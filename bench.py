@@ -408,6 +408,27 @@ class HostRolloutSource:
       yield out
 
 
+def concurrent_h2d_gbps(host_array, device, world, nbytes=2 << 30):
+  """GB/s of a pinned-host -> device copy issued by every rank at the same moment."""
+  src = torch.from_numpy(host_array).reshape(-1).view(torch.uint8)[:nbytes]
+  dst = torch.empty(src.numel(), dtype=torch.uint8, device=device)
+  dst.copy_(src[:dst.numel()], non_blocking=True)   # warm-up
+  torch.cuda.synchronize()
+  if world > 1:
+    torch.distributed.barrier()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  start.record()
+  dst.copy_(src, non_blocking=True)
+  stop.record()
+  torch.cuda.synchronize()
+  gbps = src.numel() / start.elapsed_time(stop) / 1e6
+  if world > 1:
+    t = torch.tensor([gbps], device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    gbps = float(t)
+  return gbps
+
+
 def one_update(alg, runner_iter, nbatches):
   losses = []
   for _ in range(nbatches):
@@ -622,8 +643,9 @@ def run_ours(args, rank, world, local):
               "normalize": 8.0 * mb_rows}
   if args.net == "tf32":   # stem kernels per micro-batch chunk (algorithmic bytes)
     chunk = min(args.micro_batch, mb_rows)
-    per_elem["stem_conv_relu"] = (OBS_ROW_BYTES + 400 * 32 * 4.0) * chunk
-    per_elem["stem_backward"] = (OBS_ROW_BYTES + 2 * 400 * 32 * 4.0) * chunk
+    # K6t: frame in, fp32 activation + 1-bit ReLU mask out; K7t: frame + gradient + mask in
+    per_elem["stem_conv_relu"] = (OBS_ROW_BYTES + 400 * 32 * 4.0 + 1600) * chunk
+    per_elem["stem_backward"] = (OBS_ROW_BYTES + 400 * 32 * 4.0 + 1600) * chunk
     # K5 serves the 64x9x9 and 64x7x7 activations in turn: mean bytes of the two launches
     per_elem["relu_bwd_bias"] = 12.0 * chunk * 64 * (81 + 49) / 2
   for name, (n, ms) in ktimes.items():
@@ -697,10 +719,18 @@ def run_ours(args, rank, world, local):
     alg_h, runner_h = build_alg(args, d, host_source, world, device)
     sec_h, _ = timed_updates(alg_h, runner_h, nbatches, args.steps, 1, world, True)
     perm_bytes = args.epochs * horizon * nenvs * 8
+    # what the host can feed: every rank copies 2 GiB pinned -> device at the same time (all
+    # GPUs of a box pull through the same host memory system), min over ranks
+    h2d_gbps = concurrent_h2d_gbps(host_source.host["observations"], device, world)
+    h2d_total = world * (host_source.bytes + perm_bytes)
     e2e = {"value": samples_per_step * args.steps / sec_h, "unit": "samples/s",
-           "h2d_bytes_per_step": world * (host_source.bytes + perm_bytes),
+           "h2d_bytes_per_step": h2d_total,
            "d2h_bytes_per_step": world * (nenvs * 4 + nbatches * 4),
-           "ms_per_step": sec_h / args.steps * 1e3}
+           "ms_per_step": sec_h / args.steps * 1e3,
+           "h2d_GBps_per_gpu_concurrent": h2d_gbps,
+           "h2d_floor_ms_per_step": h2d_total / world / h2d_gbps / 1e6,
+           "note": "the upload is overlapped with the first epoch (HostColumn); e2e - value is "
+                   "bounded below by (h2d floor - one epoch of compute)"}
     del host_source, alg_h, runner_h
 
   # free the big rollouts before the side measurements

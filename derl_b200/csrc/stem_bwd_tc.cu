@@ -22,14 +22,15 @@
 //   * per frame 4 quadrants x 14 K-steps of  D_q[64 taps x 64 (plane, channel)] += A * Gq^T
 //     (M = 64, N = 64, K = 32), issued by one thread; an accumulator row (a tap) holds both digit
 //     planes of all 32 channels, so the thread that owns it recombines and scales them;
-//   * the ReLU mask arrives as 1 bit per activation (written by K6t), not as the fp32 tensor.
-// Per frame HBM reads: 28 224 (frame) + 51 200 (gradient) + 1 600 (mask) = 81 KB (K7: 130.6 KB).
+//   * the ReLU mask arrives as 1 bit per activation (written by K6t with warp ballots, one word
+//     per (32 padded pixels, channel)), not as the fp32 tensor.
+// Per frame HBM reads: 28 224 (frame) + 51 200 (gradient) + 1 792 (mask) = 81 KB (K7: 130.6 KB).
 //
 // Roles (576 threads, one persistent CTA per SM): warps 0-15 are workers — quantise frame f+1,
 // then fold frame f's accumulators into their running sums (worker w owns quadrant w / 4 and the
-// tensor-memory lane quarter w % 4 = tap row i) — warp 16 = TMA producer (frames double
-// buffered, gradient tile + mask single buffered: the workers copy them to registers first
-// thing), warp 17 = MMA issuer + TMEM owner.  MMAs of frame f overlap the quantisation of f+1.
+// tensor-memory lane quarter w % 4 = tap row i) — warp 16 = TMA producer (frames, gradient tiles
+// and mask words all double buffered), warp 17 = MMA issuer + TMEM owner.  MMAs of frame f
+// overlap the quantisation of f+1.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -51,26 +52,27 @@ constexpr int kKSteps = 14;                    // 448 padded pixels / 32
 constexpr int kGroups = 28;                    // 16-pixel groups (k16 units); 27 hold pixels
 constexpr int kGqBytes = kGroups * 64 * 16;    // 28672
 constexpr int kGradBytes = kPix * kCh * 4;     // 51200
-constexpr int kMaskBytes = kPix * 4;           // 1600
+constexpr int kMaskBytes = 14 * 32 * 4;        // 1792: [tile of 32 padded pixels][channel] words
 constexpr int kWorkers = 16, kWorkerThreads = kWorkers * 32;
 constexpr int kThreads = kWorkerThreads + 64;
 constexpr int kPartial = 4 * 64 * kCh;
 constexpr uint32_t kTmemCols = 512;
 
+constexpr int kGradBuf = kGradBytes + kMaskBytes;   // gradient tile + mask words, one buffer
 struct BtSmem {   // byte offsets from a 128-aligned base
   static constexpr int frame = 0;                              // [2][29824]
-  static constexpr int grad = frame + 2 * kFrameBuf;           // 51200
-  static constexpr int mask = grad + kGradBytes;               // 1600 (+64 pad)
-  static constexpr int gq = mask + 1664;                       // [2][28672]
+  static constexpr int grad = frame + 2 * kFrameBuf;           // [2][51200 tile | 1792 mask]
+  static constexpr int gq = grad + 2 * kGradBuf;               // [2][28672]
   static constexpr int red = gq + 2 * kGqBytes;                // float [2][16][32]
   static constexpr int scale = red + 2 * kWorkers * kCh * 4;   // float [2][32]
-  static constexpr int bars = scale + 2 * kCh * 4;             // 14 mbarriers
-  static constexpr int slot = bars + 14 * 8;
+  static constexpr int table = scale + 2 * kCh * 4;            // unsigned [28 * 16] pixel table
+  static constexpr int bars = table + 28 * 16 * 4;             // 16 mbarriers
+  static constexpr int slot = bars + 16 * 8;
   static constexpr int bytes = slot + 16;
   static constexpr int alloc = bytes + 128;
 };
-static_assert(BtSmem::grad % 128 == 0 && BtSmem::mask % 16 == 0 && BtSmem::gq % 128 == 0,
-              "smem alignment");
+static_assert(BtSmem::grad % 128 == 0 && kGradBuf % 128 == 0 && BtSmem::gq % 128 == 0 &&
+                  BtSmem::bars % 8 == 0, "smem alignment");
 static_assert(BtSmem::alloc <= 227 * 1024, "shared memory budget");
 
 // A = frame taps (u8, MN-major), B = gradient digits (s8, K-major), D = int32 [64 x 64]
@@ -93,8 +95,7 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
-  const float* grad_sm = reinterpret_cast<const float*>(smem + BtSmem::grad);
-  const unsigned* mask_sm = reinterpret_cast<const unsigned*>(smem + BtSmem::mask);
+  unsigned* table = reinterpret_cast<unsigned*>(smem + BtSmem::table);
   uint8_t* gq = smem + BtSmem::gq;
   float* red = reinterpret_cast<float*>(smem + BtSmem::red);
   float* scale = reinterpret_cast<float*>(smem + BtSmem::scale);
@@ -105,8 +106,8 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
   uint64_t* gq_empty = bars + 6;        // [2] MMA -> workers
   uint64_t* tfull = bars + 8;           // [2] MMA -> workers
   uint64_t* tempty = bars + 10;         // [2] workers -> MMA (16 warp arrivals)
-  uint64_t* grad_full = bars + 12;      // TMA -> workers
-  uint64_t* grad_empty = bars + 13;     // workers -> TMA (16 warp arrivals)
+  uint64_t* grad_full = bars + 12;      // [2] TMA -> workers
+  uint64_t* grad_empty = bars + 14;     // [2] workers -> TMA (16 warp arrivals)
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + BtSmem::slot);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long first = blockIdx.x, stride = gridDim.x;
@@ -121,8 +122,10 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kWorkers);
     }
-    mbar_init(grad_full, 1);
-    mbar_init(grad_empty, kWorkers);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&grad_full[i], 1);
+      mbar_init(&grad_empty[i], kWorkers);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tm_frames);
   }
@@ -130,6 +133,18 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
   // digit buffers start as zeros: group 27 and the tail of group 26 are never written again
   for (int i = tid; i < 2 * kGqBytes / 16; i += kThreads) {
     reinterpret_cast<uint4*>(gq)[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // padded pixel m = 21 oy + ox -> float offset of its row in the gradient tile (plain or
+  // space-to-depth(2) order).  The junk column and the tail point at row 0: their mask bits are 0.
+  for (int m = tid; m < kGroups * 16; m += kThreads) {
+    const int oy = m / 21, ox = m - oy * 21;
+    unsigned entry = 0u;
+    if (m < kPixPad && ox < 20) {
+      const int row = blocked ? ((((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1))
+                              : oy * 20 + ox;
+      entry = (unsigned)(row * kCh);
+    }
+    table[m] = entry;
   }
   fence_proxy_async_smem();
   tcgen05_fence_before();
@@ -148,10 +163,11 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
         const long long src = rows ? __ldg(rows + f) : f;
         tma_load_4d(smem + BtSmem::frame + b * kFrameBuf, &tm_frames, 0, 0, 0, (int)src,
                     &frame_full[b]);
-        mbar_wait(grad_empty, (unsigned)((it & 1) ^ 1));
-        mbar_expect_tx(grad_full, kGradBytes + kMaskBytes);
-        bulk_g2s(smem + BtSmem::grad, grad_out + f * (kPix * kCh), kGradBytes, grad_full);
-        bulk_g2s(smem + BtSmem::mask, mask + f * kPix, kMaskBytes, grad_full);
+        mbar_wait(&grad_empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(&grad_full[b], kGradBytes + kMaskBytes);
+        uint8_t* gbuf = smem + BtSmem::grad + b * kGradBuf;
+        bulk_g2s(gbuf, grad_out + f * (kPix * kCh), kGradBytes, &grad_full[b]);
+        bulk_g2s(gbuf + kGradBytes, mask + f * (kMaskBytes / 4), kMaskBytes, &grad_full[b]);
       }
     }
     __syncwarp();
@@ -188,38 +204,47 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
     // ===================================================================== workers
     const int ch = lane;                       // quantiser role: one channel per lane
     const int quad = warp >> 2, quarter = warp & 3;   // accumulator role
-    float wsum[kCh];
+    float wsum[16];   // [row select][rep][h]: rows t/4 (+8), channels 8 rep + 2 (t % 4) + h
 #pragma unroll
-    for (int k = 0; k < kCh; ++k) wsum[k] = 0.f;
+    for (int k = 0; k < 16; ++k) wsum[k] = 0.f;
     float bsum = 0.f;
 
     auto quantise_frame = [&](int it) {
       const int b = it & 1;
       float v[2][16];
-      mbar_wait(grad_full, (unsigned)(it & 1));
+      const float* grad_sm = reinterpret_cast<const float*>(smem + BtSmem::grad + b * kGradBuf);
+      const unsigned* mask_sm = reinterpret_cast<const unsigned*>(
+          smem + BtSmem::grad + b * kGradBuf + kGradBytes);
+      mbar_wait(&grad_full[b], (unsigned)((it >> 1) & 1));
       float vmax = 0.f, vsum = 0.f;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int group = warp + kWorkers * k;
+        const int group = warp + kWorkers * k;      // warp-uniform; groups >= 27 hold no pixel
+        if (group < kGroups - 1) {
+          // this channel's ReLU bits of the 16 pixels: half of a 32-pixel mask word
+          const unsigned bits = mask_sm[(group >> 1) * kCh + ch] >> ((group & 1) * 16);
+          const uint4* tab = reinterpret_cast<const uint4*>(table + group * 16);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int m = group * 16 + e;
-          const int oy = m / 21, ox = m - oy * 21;
-          float g = 0.f;
-          if (group < kGroups - 1 && m < kPixPad && ox < 20) {
-            const int pixel = oy * 20 + ox;
-            const int row = blocked ? ((((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1))
-                                    : pixel;
-            const float x = grad_sm[row * kCh + ch];
-            g = (mask_sm[pixel] >> ch) & 1u ? x : 0.f;
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const uint4 off = tab[e4];                // broadcast: 4 row offsets per load
+            const unsigned o[4] = {off.x, off.y, off.z, off.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 4 * e4 + j;
+              const float x = grad_sm[o[j] + ch];
+              const float g = (bits >> e) & 1u ? x : 0.f;
+              v[k][e] = g;
+              vmax = fmaxf(vmax, fabsf(g));
+              vsum += g;
+            }
           }
-          v[k][e] = g;
-          vmax = fmaxf(vmax, fabsf(g));
-          vsum += g;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[k][e] = 0.f;
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(grad_empty);      // the tile is in registers: refill it
+      if (lane == 0) mbar_arrive(&grad_empty[b]);  // the tile is in registers: refill the buffer
       bsum += vsum;
       float* r = red + (it & 1) * (kWorkers * kCh);
       r[warp * kCh + ch] = vmax;
@@ -229,7 +254,7 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
       for (int k = 1; k < kWorkers; ++k) mx = fmaxf(mx, r[k * kCh + ch]);
       const float s = mx > 0.f ? mx / 127.f : 1.f, inv = 1.f / s;
       mbar_wait(&gq_empty[b], (unsigned)(((it >> 1) & 1) ^ 1));   // MMAs of frame it-2 have read it
-      if (warp == 0) scale[b * kCh + ch] = s;
+      if (warp == 0) scale[b * kCh + ch] = s * (1.f / 254.f);   // folds (q1 * 254 + q2) back
       uint8_t* out = gq + b * kGqBytes;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -259,23 +284,29 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
       const int b = it & 1;
       mbar_wait(&tfull[b], (unsigned)((it >> 1) & 1));
       tcgen05_fence_after();
+      // the M = 64 accumulator of quadrant `quad` occupies lanes 0-15 of every 32-lane quarter
+      // (row = 16 quarter + lane): the 16x256b fragment spreads those 16 rows x 64 columns over
+      // all 32 threads — thread t: rows t/4 and t/4 + 8, columns 8 rep + 2 (t % 4) + {0, 1}.
+      // Columns c and 32 + c (the two digit planes of channel c) land in the same thread.
       const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + quad * 64);
-      const float* sc = scale + b * kCh;
+      uint32_t v[32];
+      tmem_ld_16x256x8(taddr, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+      const float* sc = scale + b * kCh + 2 * (lane & 3);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {          // 16 channels at a time: 32 live temporaries
-        uint32_t v1[16], v2[16];
-        tmem_ld_32x16(taddr + 16 * half, v1);          // digit plane 1, channels 16 half ..
-        tmem_ld_32x16(taddr + 32 + 16 * half, v2);     // digit plane 2
-        tmem_ld_wait();
-        if (half == 1) {                               // every column has been read
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[b]);
-        }
+      for (int rep = 0; rep < 4; ++rep) {
+        const float2 s2 = *reinterpret_cast<const float2*>(sc + 8 * rep);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float x = (float)(int)v1[k] + (float)(int)v2[k] * (1.f / 254.f);
-          wsum[16 * half + k] += x * sc[16 * half + k];
+        for (int rs = 0; rs < 2; ++rs) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // exact: |acc1 * 254 + acc2| <= 256 * 255 * 127 * 255 < 2^31
+            const int both = (int)v[4 * rep + 2 * rs + h] * 254 + (int)v[4 * (rep + 4) + 2 * rs + h];
+            wsum[(rs * 4 + rep) * 2 + h] += (float)both * (h ? s2.y : s2.x);
+          }
         }
       }
     };
@@ -287,12 +318,14 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
     }
 
     // ---- per-CTA partials: partial_w[cta][quadrant][tap = 16 i + 4 j + c][channel]
-    if (lane < 16) {   // M = 64 accumulators occupy lanes 0-15 of each quarter: row = 16 quarter + lane
-      float* pw = partial_w + (size_t)blockIdx.x * kPartial +
-                  (size_t)(quad * 64 + quarter * 16 + lane) * kCh;
 #pragma unroll
-      for (int k = 0; k < kCh; k += 4) {
-        *reinterpret_cast<float4*>(pw + k) = make_float4(wsum[k], wsum[k + 1], wsum[k + 2], wsum[k + 3]);
+    for (int rs = 0; rs < 2; ++rs) {
+      float* pw = partial_w + (size_t)blockIdx.x * kPartial +
+                  (size_t)(quad * 64 + quarter * 16 + (lane >> 2) + 8 * rs) * kCh + 2 * (lane & 3);
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep) {
+        *reinterpret_cast<float2*>(pw + 8 * rep) =
+            make_float2(wsum[(rs * 4 + rep) * 2], wsum[(rs * 4 + rep) * 2 + 1]);
       }
     }
     named_bar_sync(1, kWorkerThreads);

@@ -23,8 +23,8 @@
 // bias and ReLU and holds the pixel's 128 output bytes — written to a 128B-swizzled staging tile
 // (conflict-free) that a TMA tensor store drains as two 25.6 KB boxes per frame.
 //
-// Roles (384 threads, one persistent CTA per SM): warp 0 = TMA producer (frames, double
-// buffered), warp 1 = MMA issuer + TMEM owner, warps 4-7 / 8-11 = two epilogue groups taking
+// Roles (384 threads, one persistent CTA per SM): warp 0 = TMA producer (frames, three
+// buffers: HBM latency is ~a frame period, so loads run two frames ahead), warp 1 = MMA issuer + TMEM owner, warps 4-7 / 8-11 = two epilogue groups taking
 // alternate frames (each owns one 256-column accumulator buffer and one staging tile), so that
 // frame f+1's loads and MMAs and frame f's epilogue and frame f-1's store overlap.
 #include <cuda.h>
@@ -43,16 +43,17 @@ constexpr int kMTiles = 4;                    // 4 x 128 rows
 constexpr int kWBytes = 16 * 64 * 16;         // [k16][n'][16 B]
 constexpr int kStageBytes = 400 * 128;        // one frame's fp32 activation
 constexpr int kThreads = 384;
+constexpr int kStages = 3;                    // frame buffers: loads run two frames ahead of the MMAs
 constexpr uint32_t kTmemCols = 512;
 
 struct TcSmem {   // byte offsets from a 1024-aligned base
   static constexpr int stage = 0;                              // [2][51200]
-  static constexpr int frame = stage + 2 * kStageBytes;        // [2][29824]
-  static constexpr int w = frame + 2 * kFrameBuf;              // 16384
+  static constexpr int frame = stage + 2 * kStageBytes;        // [kStages][29824]
+  static constexpr int w = frame + kStages * kFrameBuf;        // 16384
   static constexpr int scale = w + kWBytes;                    // float[32]
   static constexpr int bias = scale + 128;                     // float[32]
-  static constexpr int bars = bias + 128;                      // 8 mbarriers
-  static constexpr int slot = bars + 64;                       // tmem base address
+  static constexpr int bars = bias + 128;                      // 2 * kStages + 4 mbarriers
+  static constexpr int slot = bars + 128;                      // tmem base address
   static constexpr int bytes = slot + 16;
   static constexpr int alloc = bytes + 1024;                   // slack for the manual alignment
 };
@@ -78,18 +79,20 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
   uint8_t* wsm = smem + TcSmem::w;
   float* ssm = reinterpret_cast<float*>(smem + TcSmem::scale);
   float* bsm = reinterpret_cast<float*>(smem + TcSmem::bias);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);   // TMA -> MMA
-  uint64_t* empty = full + 2;                                          // MMA -> TMA
-  uint64_t* tfull = full + 4;                                          // MMA -> epilogue
-  uint64_t* tempty = full + 6;                                         // epilogue -> MMA
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);   // [kStages] TMA -> MMA
+  uint64_t* empty = full + kStages;                                    // [kStages] MMA -> TMA
+  uint64_t* tfull = full + 2 * kStages;                                // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                                        // [2] epilogue -> MMA
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + TcSmem::slot);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long first = blockIdx.x, stride = gridDim.x;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
     }
@@ -143,8 +146,8 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
     if (lane == 0) {
       int it = 0;
       for (long long f = first; f < batch; f += stride, ++it) {
-        const int b = it & 1;
-        mbar_wait(&empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
+        const int b = it % kStages;
+        mbar_wait(&empty[b], (unsigned)(((it / kStages) & 1) ^ 1));
         mbar_expect_tx(&full[b], kImgBytes);
         const long long src = rows ? __ldg(rows + f) : f;   // fused minibatch gather
         tma_load_4d(smem + TcSmem::frame + b * kFrameBuf, &tm_frames, 0, 0, 0, (int)src, &full[b]);
@@ -157,10 +160,10 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
       const uint32_t w_addr = smem_u32(wsm);
       int it = 0;
       for (long long f = first; f < batch; f += stride, ++it) {
-        const int b = it & 1, g = it & 1;
+        const int b = it % kStages, g = it & 1;
         const unsigned ph = (unsigned)((it >> 1) & 1);
         mbar_wait(&tempty[g], ph ^ 1u);     // the epilogue has drained this accumulator buffer
-        mbar_wait(&full[b], ph);            // the frame has landed
+        mbar_wait(&full[b], (unsigned)((it / kStages) & 1));   // the frame has landed
         tcgen05_fence_after();
         const uint32_t f_addr = smem_u32(smem + TcSmem::frame + b * kFrameBuf);
 #pragma unroll 1
@@ -210,9 +213,8 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
         const int oy = m / 21, ox = m - oy * 21;
         const bool valid = m < kPixPad && ox < 20;
         int row = oy * 20 + ox;
-        const int pixel = row;
         if (out_block == 2) row = (((oy >> 1) * 10 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
-        unsigned bits = 0u;
+        unsigned bits = 0u;       // lane c ends up with channel c's bits of this warp's 32 pixels
         uint8_t* dst = stage + row * 128;
         const int sw = row & 7;
 #pragma unroll
@@ -224,14 +226,20 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
             const float sc = ssm[ch] * inv255;
             float x = ((float)(int)v1[ch] + (float)(int)v2[ch] * inv254) * sc + bsm[ch];
             x = fmaxf(x, 0.f);
-            bits |= (x > 0.f ? 1u : 0u) << ch;
+            if (mask_out != nullptr) {            // kernel-uniform
+              const unsigned word = __ballot_sync(0xffffffffu, valid && x > 0.f);
+              bits = lane == ch ? word : bits;
+            }
             y[k] = x;
           }
           if (valid) {
             *reinterpret_cast<float4*>(dst + ((c4 ^ sw) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
           }
         }
-        if (valid && mask_out != nullptr) mask_out[f * 400 + pixel] = bits;
+        // mask words [frame][tile of 32 padded pixels (14)][channel (32)]: one coalesced 128-byte
+        // store per warp and tile; tiles 14, 15 (m >= 448) hold no pixel
+        const int tile32 = mt * 4 + wq;
+        if (mask_out != nullptr && tile32 < 14) mask_out[(f * 14 + tile32) * 32 + lane] = bits;
       }
       tcgen05_fence_before();
       mbar_arrive(&tempty[g]);               // accumulator buffer g may be overwritten

@@ -420,8 +420,8 @@ def _(frames, grad_out, out, blocked, rows=None):
 def stem_conv_relu_mask(frames: Tensor, weight: Tensor, bias: Tensor, out_block: int = 1,
                         rows: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
   """K6t (tcgen05 + tensor memory): float32 `stem_conv_relu` that also returns the ReLU mask,
-  uint32 [B, 400] with bit c of word (oy * 20 + ox) = (activation of channel c > 0) — what
-  `stem_backward_masked` reads instead of the 32x larger float32 activation."""
+  int32 [B, 14, 32]: bit l of word (t, c) = (channel c at padded pixel 21 oy + ox = 32 t + l is
+  > 0) — what `stem_backward_masked` reads instead of the 32x larger float32 activation."""
   _dense(frames, "frames", (torch.uint8,))
   batch = _check_rows(frames, rows)
   _need(tuple(frames.shape[1:]) == (84, 84, 4), f"frames must be [B,84,84,4], got {tuple(frames.shape)}")
@@ -432,7 +432,7 @@ def stem_conv_relu_mask(frames: Tensor, weight: Tensor, bias: Tensor, out_block:
   _need(out_block in (1, 2), "out_block must be 1 or 2")
   shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
   out = torch.empty(shape, dtype=torch.float32, device=frames.device)
-  mask = torch.empty((batch, 400), dtype=torch.int32, device=frames.device)
+  mask = torch.empty((batch, 14, 32), dtype=torch.int32, device=frames.device)
   with _device_of(frames, "stem_conv_relu"):
     _lib.check(_lib.load().derl_b200_stem_conv_relu_mask(
         _p(frames), _p(rows) if rows is not None else None, batch, _p(weight), _p(bias), _p(out),
@@ -445,7 +445,7 @@ def _(frames, weight, bias, out_block=1, rows=None):
   batch = frames.shape[0] if rows is None else rows.shape[0]
   shape = (batch, 20, 20, 32) if out_block == 1 else (batch, 10, 10, 128)
   return (frames.new_empty(shape, dtype=torch.float32),
-          frames.new_empty((batch, 400), dtype=torch.int32))
+          frames.new_empty((batch, 14, 32), dtype=torch.int32))
 
 
 @torch.library.custom_op("derl_b200::stem_backward_masked", mutates_args=(), device_types="cuda")
@@ -463,7 +463,7 @@ def stem_backward_masked(frames: Tensor, grad_out: Tensor, mask: Tensor, blocked
         and grad_out.is_contiguous(memory_format=torch.channels_last),
         f"grad_out must be a channels_last float32 tensor of shape {want}")
   _dense(mask, "mask", (torch.int32,))
-  _need(tuple(mask.shape) == (batch, 400), f"mask must be int32 [{batch}, 400]")
+  _need(tuple(mask.shape) == (batch, 14, 32), f"mask must be int32 [{batch}, 14, 32]")
   grad_w = torch.empty((32, 4, 8, 8), dtype=torch.float32, device=frames.device)
   grad_b = torch.empty(32, dtype=torch.float32, device=frames.device)
   lib = _lib.load()

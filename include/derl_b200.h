@@ -308,8 +308,9 @@ int derl_b200_gae_host(const void* rewards_host, int rewards_f64, const float* v
  * The two entry points below are the pair a training step uses: the forward additionally emits
  * the ReLU mask as one bit per activation, and the backward consumes that mask instead of
  * re-reading the float32 activation (51 200 B per frame less HBM traffic).
- *   relu_mask [batch, 400] uint32: bit c of word (oy * 20 + ox) = (out[pixel, channel c] > 0),
- *     pixels in plain order whatever out_block / blocked says.
+ *   relu_mask [batch, 14, 32] uint32: bit l of word (tile t, channel c) = (activation of channel c
+ *     at padded pixel m = 32 t + l is > 0), m = 21 oy + ox (ox = 20 and m >= 420 are padding,
+ *     bits 0), whatever out_block / blocked says.
  *   out must be 128-byte aligned (TMA store); everything else as in derl_b200_stem_conv_relu /
  *   derl_b200_stem_backward (derl/models.py:102-103,117-123 forward; its autograd backward). */
 int derl_b200_stem_conv_relu_mask(const uint8_t* frames_dev, const int64_t* rows_dev, int64_t batch,

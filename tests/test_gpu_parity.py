@@ -1397,3 +1397,90 @@ def test_stem_tcgen05_kernel_is_deterministic_under_repetition():
     for _ in range(30):
       again = K.stem_conv_relu(frames, weight, bias, torch.float32, 2, None)
       assert torch.equal(again, ref)
+
+
+def _expected_relu_mask(plain_out):
+  """[B, 14, 32] words of derl_b200_stem_conv_relu_mask from the plain [B, 20, 20, 32] activation:
+  bit l of (tile t, channel c) = out > 0 at padded pixel 21 oy + ox = 32 t + l."""
+  batch = plain_out.shape[0]
+  m = torch.arange(448, device=plain_out.device)
+  oy, ox = m // 21, m % 21
+  valid = (m < 420) & (ox < 20)
+  pos = torch.zeros(batch, 448, 32, dtype=torch.int64, device=plain_out.device)
+  pos[:, valid] = (plain_out[:, oy[valid], ox[valid], :] > 0).to(torch.int64)
+  weights = (1 << torch.arange(32, device=plain_out.device, dtype=torch.int64)).view(1, 1, 32, 1)
+  return (pos.view(batch, 14, 32, 32) * weights).sum(2)
+
+
+@pytest.mark.parametrize("blocked", [False, True])
+def test_stem_tcgen05_pair_mask_and_backward(blocked):
+  """K6t + K7t (the pair a training step uses): the forward's float32 output is the plain
+  `stem_conv_relu` output bit for bit and its ReLU mask is exactly (output > 0) in the padded
+  pixel-tile layout; the backward (tcgen05, frame as an MN-major operand, gradient digits
+  K-major, accumulators folded per frame from tensor memory) agrees with the mma.sync kernel K7
+  given the same inputs to float32 summation-order noise (1e-6 of the largest entry: both
+  accumulate the same exact per-frame integers) and with float32 autograd under the same mask
+  within K7's own tolerance (2e-4 / 1e-5)."""
+  torch.backends.cudnn.allow_tf32 = False
+  try:
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    weight = torch.randn(32, 4, 8, 8, device=DEV, generator=gen) * 0.05
+    bias = torch.randn(32, device=DEV, generator=gen) * 0.1
+    block = 2 if blocked else 1
+    for batch in (1, 4, 150, 333):
+      frames = torch.randint(0, 256, (batch, 84, 84, 4), device=DEV, dtype=torch.uint8,
+                             generator=gen)
+      out, mask = K.stem_conv_relu_mask(frames, weight, bias, block, None)
+      assert torch.equal(out, K.stem_conv_relu(frames, weight, bias, torch.float32, block, None))
+      plain = K.space_to_depth(out, 2, True) if blocked else out
+      assert torch.equal(mask.to(torch.int64) & 0xffffffff, _expected_relu_mask(plain))
+      grad = torch.randn(batch, 32, 20, 20, device=DEV, generator=gen) * \
+          torch.rand(batch, 1, 1, 1, device=DEV, generator=gen) * 1e-3
+      g_nhwc = grad.permute(0, 2, 3, 1).contiguous()
+      if blocked:
+        g_nhwc = K.space_to_depth(g_nhwc, 2, False)
+      g_in = g_nhwc.permute(0, 3, 1, 2)
+      new_w, new_b = K.stem_backward_masked(frames, g_in, mask, blocked, None)
+      old_w, old_b = K.stem_backward(frames, g_in, out.permute(0, 3, 1, 2), blocked, None)
+      scale_w, scale_b = old_w.abs().max(), old_b.abs().max()
+      assert (new_w - old_w).abs().max() <= 1e-6 * scale_w
+      assert (new_b - old_b).abs().max() <= 1e-6 * scale_b
+      inputs = frames.permute(0, 3, 1, 2).float() / 255
+      masked = grad * (plain.permute(0, 3, 1, 2) > 0)
+      want_w = torch.nn.grad.conv2d_weight(inputs, weight.shape, masked, stride=4)
+      want_b = masked.sum((0, 2, 3))
+      assert (new_w - want_w).abs().max() < 2e-4 * want_w.abs().max()
+      assert (new_b - want_b).abs().max() < 1e-5 * want_b.abs().max()
+      # fused gather: bit-identical to the materialised rows; repeated launches bit-identical
+      rows = torch.randint(0, batch, (batch + 2,), device=DEV, generator=gen)
+      out_r, mask_r = K.stem_conv_relu_mask(frames, weight, bias, block, rows)
+      g_r = g_in[rows].contiguous(memory_format=torch.channels_last)
+      a = K.stem_backward_masked(frames, g_r, mask_r, blocked, rows)
+      b = K.stem_backward_masked(frames[rows].contiguous(), g_r, mask_r, blocked, None)
+      assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+      for _ in range(5):
+        again = K.stem_backward_masked(frames, g_r, mask_r, blocked, rows)
+        assert torch.equal(again[0], a[0]) and torch.equal(again[1], a[1])
+  finally:
+    torch.backends.cudnn.allow_tf32 = True
+
+
+def test_model_routes_float32_stem_through_the_tcgen05_pair():
+  """NatureCNNModel under allow_tf32 uses K6t forward (saving the mask, not the activation) and
+  K7t backward; switching `tensor_memory` off gives the mma.sync pair, and the parameter
+  gradients of the two routes agree to 1e-6 of their scale."""
+  from derl_b200 import models
+  frames = torch.randint(0, 256, (40, 84, 84, 4), dtype=torch.uint8, device=DEV)
+  grads = []
+  for tm in (True, False):
+    models._StemConvReLU.tensor_memory = tm
+    try:
+      torch.manual_seed(0)
+      model = d.NatureCNNModel([4, 1])
+      logits, values = model(frames)
+      (logits.square().sum() + values.sum()).backward()
+      grads.append([p.grad.clone() for p in model.parameters()])
+    finally:
+      models._StemConvReLU.tensor_memory = True
+  for a, b in zip(*grads):
+    assert (a - b).abs().max() <= 1e-6 * max(b.abs().max().item(), 1e-12) + 1e-12

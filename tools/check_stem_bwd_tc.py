@@ -16,6 +16,18 @@ def s2d2(x):   # [B,20,20,32] -> [B,10,10,128]
   return K.space_to_depth(x.contiguous(), 2, False)
 
 
+def expected_mask(out):
+  """[B, 14, 32] words: bit l of (t, c) = out[b, oy, ox, c] > 0 at padded pixel 21 oy + ox = 32 t + l."""
+  batch = out.shape[0]
+  m = torch.arange(448, device=out.device)
+  oy, ox = m // 21, m % 21
+  valid = (m < 420) & (ox < 20)
+  pos = torch.zeros(batch, 448, 32, dtype=torch.int64, device=out.device)
+  pos[:, valid] = (out[:, oy[valid], ox[valid], :] > 0).to(torch.int64)
+  weights = (1 << torch.arange(32, device=out.device, dtype=torch.int64)).view(1, 1, 32, 1)
+  return (pos.view(batch, 14, 32, 32) * weights).sum(2)
+
+
 def profile_only():
   """A short run for ncu: K6t (with mask) and K7t on 8192 frames."""
   gen = torch.Generator(device="cuda").manual_seed(1)
@@ -45,9 +57,7 @@ def main():
                            generator=gen)
     out, mask = K.stem_conv_relu_mask(frames, weight.detach(), bias.detach(), 1, None)
     torch.cuda.synchronize()
-    want_mask = ((out > 0).to(torch.int64) << torch.arange(32, device="cuda")).sum(-1).reshape(batch, 400)
-    got_mask = mask.to(torch.int64) & 0xffffffff
-    mask_ok = torch.equal(got_mask, want_mask)
+    mask_ok = torch.equal(mask.to(torch.int64) & 0xffffffff, expected_mask(out))
     grad = torch.randn(batch, 20, 20, 32, device="cuda", generator=gen)
     grad[batch // 2] *= 1e-3    # a frame with small gradients: block floating point is per frame
     # float32 reference with the SAME ReLU mask (the kernels' own: a sign flip of a near-zero
