@@ -655,6 +655,19 @@ def run_ours(args, rank, world, local):
       entry["frac"] = entry["GBps"] / hbm_peak
     kernels[name] = entry
 
+  # the north-star data path alone (K1 + K2 + K3 and their helpers, no network): aggregate
+  # algorithmic bytes / summed CUDA-event time of those launches inside the timed region
+  data_path = None
+  names = [n for n in ("gae", "gather_rows", "gather_columns", "normalize", "ppo_loss_categorical")
+           if n in ktimes]
+  if names:
+    bytes_of = dict(per_elem, gather_rows=float((8 + 2 * OBS_ROW_BYTES) * mb_rows))
+    tot_ms = sum(ktimes[n][0] * ktimes[n][1] for n in names) / args.steps
+    tot_bytes = sum(ktimes[n][0] * bytes_of[n] for n in names) / args.steps
+    data_path = {"kernels": names, "ms_per_step": tot_ms, "bytes_per_step": tot_bytes,
+                 "GBps": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / hbm_peak,
+                 "share_of_step": tot_ms / (sec / args.steps * 1e3)}
+
   if args.torch_profile and rank == 0:   # diagnostic only; never part of a reported number
     from torch.profiler import ProfilerActivity, profile
     it = runner.run()
@@ -759,7 +772,8 @@ def run_ours(args, rank, world, local):
                   "bf16": "f32 params, bf16 autocast network; GAE f64 registers; u8 gather"}[args.net],
         "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_fp32": alt_fp32,
+        "roofline": roofline, "data_path": data_path, "kernels": kernels, "cpu_baseline": cpu,
+        "alt_fp32": alt_fp32,
         "alt_network": alt, "alt_fused_gather": fused,
         "last_loss": last_loss,
     }

@@ -219,7 +219,6 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
 #endif
 
     OT* dst = out + f * (long long)(kPix * kOutC);
-    const float inv255 = 1.0f / 255.0f, inv254 = 1.0f / 254.0f;
 #pragma unroll
     for (int m = 0; m < kI8Tiles; ++m) {
       if (!live[m]) continue;
@@ -233,14 +232,15 @@ stem_conv_relu_i8_kernel(const uint8_t* __restrict__ frames, const long long* __
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const int ch = n * 8 + 2 * t;
-        const float s0 = ssm[ch] * inv255, s1 = ssm[ch + 1] * inv255;
+        // (q1 * 254 + q2) * s / (254 * 255) = (q1 + q2 / 254) * s / 255: the integer sum is exact
+        // (< 2^31), one conversion, one rounding (the same arithmetic as K6t, stem_tc.cu)
+        const float s0 = ssm[ch] / 64770.f, s1 = ssm[ch + 1] / 64770.f;
         const float b0 = bsm[ch], b1 = bsm[ch + 1];
         float y[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float sc = (k & 1) ? s1 : s0;
-          y[k] = ((float)acc[m][n][0][k] + (float)acc[m][n][1][k] * inv254) * sc +
-                 ((k & 1) ? b1 : b0);
+          y[k] = (float)(acc[m][n][0][k] * 254 + acc[m][n][1][k]) * sc + ((k & 1) ? b1 : b0);
           y[k] = fmaxf(y[k], 0.f);
         }
         store2<OT>(dst + o0 + ch, y[0], y[1]);

@@ -158,16 +158,20 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
       for (int it = 0; it < nframes; ++it) {
         const long long f = first + (long long)it * stride;
         const int b = it & 1;
-        mbar_wait(&frame_empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
-        mbar_expect_tx(&frame_full[b], kImgBytes);
-        const long long src = rows ? __ldg(rows + f) : f;
-        tma_load_4d(smem + BtSmem::frame + b * kFrameBuf, &tm_frames, 0, 0, 0, (int)src,
-                    &frame_full[b]);
+        // gradient tile first: its buffer was released when the workers copied tile it-2 to
+        // registers, long before the MMAs of frame it-2 let go of the frame buffer — issuing in
+        // this order gives the 53 KB a whole frame period to arrive (the other order made the
+        // quantiser wait on HBM latency every frame: 27 % of the stall samples)
         mbar_wait(&grad_empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
         mbar_expect_tx(&grad_full[b], kGradBytes + kMaskBytes);
         uint8_t* gbuf = smem + BtSmem::grad + b * kGradBuf;
         bulk_g2s(gbuf, grad_out + f * (kPix * kCh), kGradBytes, &grad_full[b]);
         bulk_g2s(gbuf + kGradBytes, mask + f * (kMaskBytes / 4), kMaskBytes, &grad_full[b]);
+        mbar_wait(&frame_empty[b], (unsigned)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(&frame_full[b], kImgBytes);
+        const long long src = rows ? __ldg(rows + f) : f;
+        tma_load_4d(smem + BtSmem::frame + b * kFrameBuf, &tm_frames, 0, 0, 0, (int)src,
+                    &frame_full[b]);
       }
     }
     __syncwarp();

@@ -23,8 +23,8 @@
 // bias and ReLU and holds the pixel's 128 output bytes — written to a 128B-swizzled staging tile
 // (conflict-free) that a TMA tensor store drains as two 25.6 KB boxes per frame.
 //
-// Roles (384 threads, one persistent CTA per SM): warp 0 = TMA producer (frames, three
-// buffers: HBM latency is ~a frame period, so loads run two frames ahead), warp 1 = MMA issuer + TMEM owner, warps 4-7 / 8-11 = two epilogue groups taking
+// Roles (576 threads, one persistent CTA per SM): warp 0 = TMA producer (frames, three
+// buffers: HBM latency is ~a frame period, so loads run two frames ahead), warp 1 = MMA issuer + TMEM owner, warps 2-9 / 10-17 = two epilogue groups taking
 // alternate frames (each owns one 256-column accumulator buffer and one staging tile), so that
 // frame f+1's loads and MMAs and frame f's epilogue and frame f-1's store overlap.
 #include <cuda.h>
@@ -42,7 +42,8 @@ constexpr int kOutC = 32, kPixPad = 420;      // padded pixel index m = 21 oy + 
 constexpr int kMTiles = 4;                    // 4 x 128 rows
 constexpr int kWBytes = 16 * 64 * 16;         // [k16][n'][16 B]
 constexpr int kStageBytes = 400 * 128;        // one frame's fp32 activation
-constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;                  // warps per epilogue group: 4 lane quarters x 2 tile parities
+constexpr int kThreads = (2 + 2 * kEpiWarps) * 32;   // 576
 constexpr int kStages = 3;                    // frame buffers: loads run two frames ahead of the MMAs
 constexpr uint32_t kTmemCols = 512;
 
@@ -52,7 +53,8 @@ struct TcSmem {   // byte offsets from a 1024-aligned base
   static constexpr int w = frame + kStages * kFrameBuf;        // 16384
   static constexpr int scale = w + kWBytes;                    // float[32]
   static constexpr int bias = scale + 128;                     // float[32]
-  static constexpr int bars = bias + 128;                      // 2 * kStages + 4 mbarriers
+  static constexpr int escale = bias + 128;                    // float[32]: s / (254 * 255)
+  static constexpr int bars = escale + 128;                    // 2 * kStages + 4 mbarriers
   static constexpr int slot = bars + 128;                      // tmem base address
   static constexpr int bytes = slot + 16;
   static constexpr int alloc = bytes + 1024;                   // slack for the manual alignment
@@ -67,6 +69,7 @@ __device__ __forceinline__ void tma_store_2d_f(const void* tmap, const void* sme
   tma_store_2d(tmap, smem_src, c0, c1);
 }
 
+template <bool kMask>   // kMask: also emit the ReLU mask words (K7t's input)
 __global__ void __launch_bounds__(kThreads, 1)
 stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
                          const __grid_constant__ CUtensorMap tm_out,
@@ -79,6 +82,7 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
   uint8_t* wsm = smem + TcSmem::w;
   float* ssm = reinterpret_cast<float*>(smem + TcSmem::scale);
   float* bsm = reinterpret_cast<float*>(smem + TcSmem::bias);
+  float* esm = reinterpret_cast<float*>(smem + TcSmem::escale);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TcSmem::bars);   // [kStages] TMA -> MMA
   uint64_t* empty = full + kStages;                                    // [kStages] MMA -> TMA
   uint64_t* tfull = full + 2 * kStages;                                // [2] MMA -> epilogue
@@ -94,7 +98,7 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], kEpiWarps * 32);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tm_frames);
@@ -113,6 +117,8 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
   }
   if (tid < kOutC) bsm[tid] = __ldg(bias + tid);
   __syncthreads();
+  // epilogue scale s / (254 * 255): (q1 * 254 + q2) * that = (q1 + q2 / 254) * s / 255
+  if (tid < kOutC) esm[tid] = ssm[tid] / 64770.f;
   for (int e = tid; e < 16 * kOutC; e += kThreads) {
     const int n = e & 31, k16 = e >> 5;
     const int q = k16 >> 2, i = k16 & 3, kh = 4 * (q >> 1) + i, kw0 = 4 * (q & 1);
@@ -186,30 +192,30 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else {
     // ===================================================================== epilogue groups
-    const int g = (warp - 4) >> 2;            // group 0: warps 4-7, group 1: warps 8-11
-    const int wq = warp & 3;                  // tensor-memory lane quarter of this warp
-    const int gt = tid - (4 + 4 * g) * 32;    // thread index inside the group
+    // 16 warps = 2 groups (alternate frames) x 4 tensor-memory lane quarters x 2 tile parities.
+    // A warp can only read the quarter (warp id % 4) of tensor memory; the two warps of a
+    // quarter split the frame's four 128-pixel tiles between them.
+    const int e = warp - 2;
+    const int g = e / kEpiWarps;                        // group: frames with it % 2 == g
+    const int wq = warp & 3;                            // tensor-memory lane quarter
+    const int tp = (e % kEpiWarps) >> 2;                // tile parity
+    const int gt = tid - (2 + kEpiWarps * g) * 32;      // thread index inside the group
     uint8_t* stage = smem + TcSmem::stage + g * kStageBytes;
-    const float inv255 = 1.0f / 255.0f, inv254 = 1.0f / 254.0f;
     int it = 0, mine = 0;
     for (long long f = first; f < batch; f += stride, ++it) {
       if ((it & 1) != g) continue;
       const unsigned ph = (unsigned)((it >> 1) & 1);
       // the previous store of this staging tile must have finished READING it
       if (gt == 0 && mine > 0) bulk_wait_read<0>();
-      named_bar_sync(1 + g, 128);
+      named_bar_sync(1 + g, kEpiWarps * 32);
       mbar_wait(&tfull[g], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int mt = 0; mt < kMTiles; ++mt) {
+      for (int mt = tp; mt < kMTiles; mt += 2) {
         const int m = mt * 128 + wq * 32 + lane;
         const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 256 + mt * 64);
-        uint32_t v1[32], v2[32];
-        tmem_ld_32x32(taddr, v1);
-        tmem_ld_32x32(taddr + 32, v2);
-        tmem_ld_wait();
         const int oy = m / 21, ox = m - oy * 21;
         const bool valid = m < kPixPad && ox < 20;
         int row = oy * 20 + ox;
@@ -218,33 +224,46 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
         uint8_t* dst = stage + row * 128;
         const int sw = row & 7;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float y[4];
+        for (int half = 0; half < 2; ++half) {   // 16 channels at a time: 32 live accumulator words
+          uint32_t v1[16], v2[16];
+          tmem_ld_32x16(taddr + 16 * half, v1);         // digit plane 1
+          tmem_ld_32x16(taddr + 32 + 16 * half, v2);    // digit plane 2
+          tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = c4 * 4 + k;
-            const float sc = ssm[ch] * inv255;
-            float x = ((float)(int)v1[ch] + (float)(int)v2[ch] * inv254) * sc + bsm[ch];
-            x = fmaxf(x, 0.f);
-            if (mask_out != nullptr) {            // kernel-uniform
-              const unsigned word = __ballot_sync(0xffffffffu, valid && x > 0.f);
-              bits = lane == ch ? word : bits;
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int ch0 = 16 * half + 4 * c4;
+            const float4 e4 = *reinterpret_cast<const float4*>(esm + ch0);   // broadcast LDS.128
+            const float4 b4 = *reinterpret_cast<const float4*>(bsm + ch0);
+            const float es[4] = {e4.x, e4.y, e4.z, e4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+            float y[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ch = ch0 + k;
+              // exact: |q1 * 254 + q2| <= 256 * 255 * 127 * 255 < 2^31
+              const int both = (int)v1[4 * c4 + k] * 254 + (int)v2[4 * c4 + k];
+              float x = (float)both * es[k] + bs[k];
+              x = fmaxf(x, 0.f);
+              if (kMask) {
+                const unsigned word = __ballot_sync(0xffffffffu, valid && x > 0.f);
+                bits = lane == ch ? word : bits;
+              }
+              y[k] = x;
             }
-            y[k] = x;
-          }
-          if (valid) {
-            *reinterpret_cast<float4*>(dst + ((c4 ^ sw) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
+            if (valid) {
+              *reinterpret_cast<float4*>(dst + (((4 * half + c4) ^ sw) << 4)) =
+                  make_float4(y[0], y[1], y[2], y[3]);
+            }
           }
         }
         // mask words [frame][tile of 32 padded pixels (14)][channel (32)]: one coalesced 128-byte
         // store per warp and tile; tiles 14, 15 (m >= 448) hold no pixel
         const int tile32 = mt * 4 + wq;
-        if (mask_out != nullptr && tile32 < 14) mask_out[(f * 14 + tile32) * 32 + lane] = bits;
+        if (kMask && tile32 < 14) mask_out[(f * 14 + tile32) * 32 + lane] = bits;
       }
       tcgen05_fence_before();
       mbar_arrive(&tempty[g]);               // accumulator buffer g may be overwritten
       fence_proxy_async_smem();              // staging writes -> visible to the TMA store
-      named_bar_sync(1 + g, 128);
+      named_bar_sync(1 + g, kEpiWarps * 32);
       if (gt == 0) {
         tma_store_2d_f(&tm_out, stage, 0, (int)(f * 400));
         tma_store_2d_f(&tm_out, stage + 200 * 128, 0, (int)(f * 400 + 200));
@@ -336,13 +355,12 @@ int launch_stem_tc(const uint8_t* frames, const long long* rows, long long batch
     set_error("stem_conv_relu: cuTensorMapEncodeTiled failed (batch %lld)", batch);
     return DERL_E_CUDA;
   }
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(stem_conv_relu_tc_kernel),
-                                   TcSmem::alloc))
-    return rc;
+  auto kern = mask_out != nullptr ? stem_conv_relu_tc_kernel<true> : stem_conv_relu_tc_kernel<false>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), TcSmem::alloc)) return rc;
   long long grid = sm_count();
   if (grid > batch) grid = batch;
-  stem_conv_relu_tc_kernel<<<(unsigned)grid, kThreads, TcSmem::alloc, st>>>(
-      tm_frames, tm_out, rows, weight, bias, mask_out, batch, out_block);
+  kern<<<(unsigned)grid, kThreads, TcSmem::alloc, st>>>(tm_frames, tm_out, rows, weight, bias,
+                                                        mask_out, batch, out_block);
   DERL_LAUNCH_CHECK("stem_conv_relu_tc_kernel");
   return DERL_OK;
 }

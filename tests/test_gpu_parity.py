@@ -589,7 +589,7 @@ def test_ppo_pybullet_fixture_through_the_product_model(golden):
                                err_msg=f"grad_{j}")
 
 
-def run_golden_update(g, kind, micro_batch=None, fused_gather=False):
+def run_golden_update(g, kind, micro_batch=None, fused_gather=False, graphed_warmup=None):
   """The golden rollouts through the whole drop-in pipeline (GAE -> minibatches -> normalise ->
   fused loss -> backward -> clip -> Adam) with the reference's seeds; returns (losses, model)."""
   torch.manual_seed(0)
@@ -623,8 +623,14 @@ def run_golden_update(g, kind, micro_batch=None, fused_gather=False):
                              num_minibatches=int(g["nmb"]))
   if fused_gather:
     runner.runner.fused_gather = True
-  optimizer = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), eps=1e-5)
-  trainer = d.Trainer(optimizer, max_grad_norm=.5, micro_batch=micro_batch)
+  if graphed_warmup is None:
+    optimizer = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), eps=1e-5)
+    trainer = d.Trainer(optimizer, max_grad_norm=.5, micro_batch=micro_batch)
+  else:   # CUDA-graph replay of the step after `graphed_warmup` eager steps per minibatch shape
+    lr = d.LinearAnneal(float(g["lr"]), 10 ** 12, device=DEV)
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr.get_tensor(), eps=1e-5, capturable=True)
+    trainer = d.GraphedTrainer(optimizer, anneals=[lr], max_grad_norm=.5, warmup=graphed_warmup)
+  run_golden_update.trainer = trainer
   alg = d.PPO(runner, trainer, cliprange=float(g["cliprange"]),
               value_loss_coef=float(g["value_loss_coef"]), entropy_coef=float(g["entropy_coef"]))
   np.random.seed(int(g["seed"]))
@@ -648,6 +654,26 @@ def test_full_ppo_update_matches_reference_losses(golden, name, kind):
   np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
   final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
   # a sum over 1.7 M parameters with cancellation: 1e-4 of the sum is ~1e-8 per parameter
+  np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("name,kind", [("live_update_mujoco.npz", "mujoco"),
+                                       ("live_update_atari.npz", "atari")])
+def test_graph_replayed_update_matches_reference_losses(golden, name, kind):
+  """GraphedTrainer (forward + fused loss + backward + clip + capturable Adam
+  captured once per minibatch shape, then replayed) against the ORACLE, not against the eager
+  path: the reference's golden loss sequence and final parameter sum, at the tolerance of the
+  eager float32 test.  One eager warm-up step per shape, every later step is a graph replay."""
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.backends.cudnn.allow_tf32 = False
+  try:
+    g = golden(name)
+    losses, model = run_golden_update(g, kind, graphed_warmup=1)
+  finally:
+    torch.backends.cudnn.allow_tf32 = True
+  assert run_golden_update.trainer.replays == len(losses) - 1
+  np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
+  final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
   np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-4)
 
 
