@@ -341,7 +341,7 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------ our arm
-def build_alg(args, d, source, world, device):
+def build_alg(args, d, source, world, device, graphed=False):
   model = source.policy.model
   sync = None
   group_norm = None
@@ -354,6 +354,16 @@ def build_alg(args, d, source, world, device):
   runner = d.TransformInteractions(source, transforms)
   runner = d.IterateWithMinibatches(runner, args.epochs, args.minibatches)
   runner = d.TransformInteractions(runner, [d.NormalizeAdvantages(group=group_norm)])
+  if graphed:   # CUDA-graph replay of the micro-batched step, frames fed by index (fused gather)
+    runner.runner.fused_gather = True
+    anneal_t = d.LinearAnneal(HP["lr"], 10e6 * 100, name="lr", device=device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=anneal_t.get_tensor(), eps=HP["eps"],
+                                 capturable=True)
+    trainer = d.GraphedTrainer(optimizer, anneals=[anneal_t], max_grad_norm=HP["max_grad_norm"],
+                               grad_sync=sync, micro_batch=args.micro_batch)
+    alg = d.PPO(runner, trainer, cliprange=HP["cliprange"],
+                value_loss_coef=HP["value_loss_coef"], entropy_coef=HP["entropy_coef"])
+    return alg, runner
   optimizer = torch.optim.Adam(model.parameters(), lr=HP["lr"], eps=HP["eps"], fused=True)
   anneal = d.LinearAnneal(HP["lr"], 10e6 * 100, name="lr")
 
@@ -718,6 +728,19 @@ def run_ours(args, rank, world, local):
              "value": samples_per_step * alt_steps / sec_f, "unit": "samples/s",
              "ms_per_step": sec_f / alt_steps * 1e3, "steps": alt_steps}
 
+  # ---- informational: the same update as CUDA graphs (GraphedTrainer with micro-batches: one
+  # graph per 32768-row chunk + one update graph; frames reach the stem kernels by index)
+  graphed = None
+  if not args.no_alt and args.net == "tf32":
+    alg_g, runner_g = build_alg(args, d, source, world, device, graphed=True)
+    sec_g, _ = timed_updates(alg_g, runner_g, nbatches, alt_steps, 4, world, False)
+    graphed = {"what": "GraphedTrainer(micro_batch) + fused_gather: CUDA-graph replay of the step",
+               "value": samples_per_step * alt_steps / sec_g, "unit": "samples/s",
+               "ms_per_step": sec_g / alt_steps * 1e3, "steps": alt_steps,
+               "graph_replays": alg_g.trainer.replays}
+    del alg_g, runner_g
+    torch.cuda.empty_cache()
+
   # ---- e2e: rollout in pinned host memory, uploaded inside the timed region
   e2e = None
   import psutil
@@ -774,7 +797,7 @@ def run_ours(args, rank, world, local):
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "data_path": data_path, "kernels": kernels, "cpu_baseline": cpu,
         "alt_fp32": alt_fp32,
-        "alt_network": alt, "alt_fused_gather": fused,
+        "alt_network": alt, "alt_fused_gather": fused, "alt_graphed": graphed,
         "last_loss": last_loss,
     }
     if sweep is not None:

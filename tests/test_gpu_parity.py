@@ -629,7 +629,8 @@ def run_golden_update(g, kind, micro_batch=None, fused_gather=False, graphed_war
   else:   # CUDA-graph replay of the step after `graphed_warmup` eager steps per minibatch shape
     lr = d.LinearAnneal(float(g["lr"]), 10 ** 12, device=DEV)
     optimizer = torch.optim.Adam(model.parameters(), lr=lr.get_tensor(), eps=1e-5, capturable=True)
-    trainer = d.GraphedTrainer(optimizer, anneals=[lr], max_grad_norm=.5, warmup=graphed_warmup)
+    trainer = d.GraphedTrainer(optimizer, anneals=[lr], max_grad_norm=.5, warmup=graphed_warmup,
+                               micro_batch=micro_batch)
   run_golden_update.trainer = trainer
   alg = d.PPO(runner, trainer, cliprange=float(g["cliprange"]),
               value_loss_coef=float(g["value_loss_coef"]), entropy_coef=float(g["entropy_coef"]))
@@ -673,8 +674,42 @@ def test_graph_replayed_update_matches_reference_losses(golden, name, kind):
     torch.backends.cudnn.allow_tf32 = True
   assert run_golden_update.trainer.replays == len(losses) - 1
   np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
+  _check_param_sum(model, g)
+
+
+def _check_param_sum(model, g, tol=2e-7):
+  """|sum(p) - golden| <= tol * sum|p|.  Capturable Adam evaluates its bias corrections in
+  float32 on the device (the eager optimizer in Python doubles): ~1e-7 relative per parameter,
+  and the golden sum cancels from sum|p| = 25 771 down to -13.4."""
   final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
-  np.testing.assert_allclose(final.sum().item(), float(g["final_param_sum"]), rtol=1e-4)
+  dev = abs(final.sum().item() - float(g["final_param_sum"]))
+  assert dev <= tol * float(g["final_param_abs_sum"]), dev
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+def test_graph_replayed_micro_batched_update_with_fused_gather(golden, tf32):
+  """The large-configuration step as CUDA graphs: GraphedTrainer(micro_batch=) replays one graph
+  per row chunk (ragged: 12-row minibatches in chunks of 5) plus one update graph, and with
+  `fused_gather=True` a chunk graph's observation input is the int64 row vector, not frames.
+  float32: the reference's golden losses at the eager test's tolerance.  TF32 (the benchmarked
+  arithmetic, where the stem kernels gather rows by index inside the graph): the TF32 bounds of
+  `test_benchmarked_configuration_tracks_the_fp32_reference_losses`."""
+  torch.backends.cuda.matmul.allow_tf32 = tf32
+  torch.backends.cudnn.allow_tf32 = tf32
+  try:
+    g = golden("live_update_atari.npz")
+    losses, model = run_golden_update(g, "atari", micro_batch=5, fused_gather=True,
+                                      graphed_warmup=1)
+  finally:
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+  assert run_golden_update.trainer.replays == len(losses) - 1
+  rel = np.abs(np.asarray(losses) - g["losses"]) / np.abs(g["losses"])
+  if tf32:
+    assert rel[0] <= TF32_FIRST_LOSS_RTOL and rel.max() <= TF32_LOSS_RTOL, rel
+  else:
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-4, atol=1e-5)
+    _check_param_sum(model, g)
 
 
 # Tolerances of the benchmarked (default `bench.py`) arithmetic against the reference's float32
