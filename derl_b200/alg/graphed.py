@@ -154,9 +154,13 @@ class GraphedTrainer(Trainer):
       self._total = torch.zeros((), dtype=torch.float32, device=params[0].device)
     chunks = list(_split_rows(data, self.micro_batch))
     sigs = [self._chunk_signature(c, self.keys, w) for c, w in chunks]
-    seen = min(self._seen.get(sig, 0) for sig in sigs)
-    for sig in set(sigs):
-      self._seen[sig] = self._seen.get(sig, 0) + 1
+    # eager warm-up is per SHAPE (optimizer state, library plans); a new rollout tensor (another
+    # source pointer in the signature) only needs a new capture
+    shapes = [tuple(x[:3] if isinstance(x, tuple) and len(x) == 4 and x[1] == "rows" else x
+                    for x in sig) for sig in sigs]
+    seen = min(self._seen.get(shape, 0) for shape in shapes)
+    for shape in set(shapes):
+      self._seen[shape] = self._seen.get(shape, 0) + 1
     if seen < self.warmup:
       return Trainer.step(self, alg, data)      # eager: optimizer state, library plans, grads
     for anneal in self.anneals:
