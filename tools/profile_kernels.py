@@ -2,7 +2,7 @@
 
   python tools/profile_kernels.py                       # plain run (must exit 0 first)
   ncu --set full --clock-control none --import-source on \
-      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|gather_columns|frames_to_s2d|relu_bwd|stem_conv' -c 48 \
+      -k regex:'gather_rows_tma|gae_tma|gae_direct|ppo_loss|ppo_mlp|gather_columns|frames_to_s2d|relu_bwd|stem_' -c 80 \
       -o gpurun_out/kernels python tools/profile_kernels.py
 
 Sizes: gather = one 131072-row minibatch out of a 4096x128 frame-stack rollout (14.8 GB,
@@ -87,11 +87,23 @@ def main():
     timed(f"stem_conv_relu 32768 f32 blk{blk}",
           lambda: K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, blk),
           32768 * (28224 + 400 * 32 * 4.0))
-  act = K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, 2).permute(0, 3, 1, 2)
+  timed("stem_conv_relu_mask 32768 blk2 (K6t)",
+        lambda: K.stem_conv_relu_mask(obs[:32768], wstem, bstem, 2),
+        32768 * (28224 + 400 * 32 * 4.0 + 1792))
+  os.environ["DERL_STEM_MMA_SYNC"] = "1"
+  timed("stem_conv_relu 32768 blk2 (K6, mma.sync)",
+        lambda: K.stem_conv_relu(obs[:32768], wstem, bstem, torch.float32, 2),
+        32768 * (28224 + 400 * 32 * 4.0))
+  os.environ.pop("DERL_STEM_MMA_SYNC")
+  act, relu_mask = K.stem_conv_relu_mask(obs[:32768], wstem, bstem, 2)
+  act = act.permute(0, 3, 1, 2)
   gact = torch.randn_like(act) * 1e-3
-  timed("stem_backward 32768 blocked", lambda: K.stem_backward(obs[:32768], gact, act, True),
-        32768 * (28224 + 2 * 51200.0))
-  del act, gact
+  timed("stem_backward_masked 32768 (K7t)",
+        lambda: K.stem_backward_masked(obs[:32768], gact, relu_mask, True),
+        32768 * (28224 + 51200.0 + 1792))
+  timed("stem_backward 32768 blocked (K7, mma.sync)",
+        lambda: K.stem_backward(obs[:32768], gact, act, True), 32768 * (28224 + 2 * 51200.0))
+  del act, gact, relu_mask
   frames = obs[:16384]
   for dt, nb in ((torch.float32, 5.0), (torch.bfloat16, 3.0)):
     timed(f"frames_to_s2d 16384 {str(dt)[6:]}", lambda: K.frames_to_s2d(frames, 4, dt, 255.0),
@@ -111,6 +123,22 @@ def main():
           acts.repeat(4)]
   timed("gather_columns 5 cols", lambda: K.gather_columns(cols, perm, mb, mb, 0),
         (8 + 2 * 24.0) * mb)
+  # ---- K8: one whole MuJoCo-shaped update (2048 samples, 10 epochs x 32 minibatches of 64)
+  size, odim, adim = 2048, 17, 6
+  shapes = [(64, odim), (64,), (64, 64), (64,), (adim, 64), (adim,),
+            (64, odim), (64,), (64, 64), (64,), (1, 64), (1,), (adim,)]
+  params = [torch.randn(sh, device=DEV, generator=gen) * .1 for sh in shapes]
+  m1 = [torch.zeros_like(p) for p in params]
+  m2 = [torch.zeros_like(p) for p in params]
+  mobs = torch.randn(size, odim, device=DEV, generator=gen, dtype=torch.float64)
+  mact = torch.randn(size, adim, device=DEV, generator=gen)
+  mcol = lambda: torch.randn(size, device=DEV, generator=gen)
+  mlp, madv, mvt, mval = mcol() * .1 - 8, mcol(), mcol(), mcol()
+  mperm = torch.cat([torch.randperm(size, device=DEV, generator=gen) for _ in range(10)])
+  timed("ppo_mlp_update 2048 x 10 x 32 (K8)",
+        lambda: K.ppo_mlp_update(params, m1, m2, mobs, mact, mlp, madv, mvt, mval, mperm, 10, 64,
+                                 True, 1e-8, .2, .25, 0., .5, 3e-4, .9, .999, 1e-5, 0),
+        320 * 64 * (17 * 8 + 6 * 4 + 16.0))
 
 
 if __name__ == "__main__":
