@@ -590,6 +590,28 @@ def small_configs(d):
   return out
 
 
+def gae_sweep_cpu():
+  """The reference's GAE loop (NumPy, one core: derl/runners/trajectory_transforms.py:45-65,
+  restated in oracle/derl_oracle.py:gae) on a few points of the same sweep, float64 rewards as
+  its EnvRunner produces them (21 B per element).  Bounded: ~3 s in total."""
+  from oracle import derl_oracle as O
+  rows = []
+  rng = np.random.RandomState(0)
+  for nsteps, nenvs in ((128, 8), (128, 4096), (128, 65536), (2048, 4096)):
+    rewards = rng.standard_normal((nsteps, nenvs))
+    values = rng.standard_normal((nsteps, nenvs, 1)).astype(np.float32)
+    resets = rng.rand(nsteps, nenvs) < 0.01
+    last = rng.standard_normal((nenvs, 1)).astype(np.float32)
+    best = float("inf")
+    for _ in range(2):
+      t0 = time.perf_counter()
+      O.gae(rewards, values, resets, last, 0.99, 0.95, normalize=False)
+      best = min(best, time.perf_counter() - t0)
+    rows.append({"T": nsteps, "N": nenvs, "ms": best * 1e3,
+                 "GBps": 21.0 * nsteps * nenvs / best / 1e9, "cores": 1})
+  return rows
+
+
 def run_ours(args, rank, world, local):
   import derl_b200 as d
   from derl_b200 import _lib, ops
@@ -664,6 +686,18 @@ def run_ours(args, rank, world, local):
       entry["GBps"] = per_elem[name] / ms / 1e6
       entry["frac"] = entry["GBps"] / hbm_peak
     kernels[name] = entry
+
+  # the derl_b200 kernel that takes the most time in the step (a network-stem kernel, not one of
+  # the three north-star kernels): its roofline object, same definition as `roofline`
+  top = None
+  timed_names = [n for n in kernels if "GBps" in kernels[n]]
+  if timed_names:
+    name = max(timed_names, key=lambda n: kernels[n]["launches"] * kernels[n]["mean_ms"])
+    k = kernels[name]
+    top = {"bound": "hbm", "kernel": name, "achieved": k["GBps"], "peak": hbm_peak, "unit": "GB/s",
+           "frac": k["frac"], "traffic": None, "bytes_per_launch": per_elem[name],
+           "launch_ms": k["mean_ms"], "launches_timed": k["launches"],
+           "share_of_step": k["launches"] * k["mean_ms"] / (sec * 1e3)}
 
   # the north-star data path alone (K1 + K2 + K3 and their helpers, no network): aggregate
   # algorithmic bytes / summed CUDA-event time of those launches inside the timed region
@@ -795,13 +829,15 @@ def run_ours(args, rank, world, local):
                   "bf16": "f32 params, bf16 autocast network; GAE f64 registers; u8 gather"}[args.net],
         "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "data_path": data_path, "kernels": kernels, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_top_by_time": top, "data_path": data_path,
+        "kernels": kernels, "cpu_baseline": cpu,
         "alt_fp32": alt_fp32,
         "alt_network": alt, "alt_fused_gather": fused, "alt_graphed": graphed,
         "last_loss": last_loss,
     }
     if sweep is not None:
       line["gae_sweep"] = sweep
+      line["gae_sweep_cpu"] = gae_sweep_cpu()
     if small is not None:
       line["small_configs"] = small
     print(json.dumps(line), flush=True)

@@ -226,7 +226,73 @@ int check_common(const char* who, long long B, const void* head, const float* ol
   return DERL_OK;
 }
 
+// One body for the PPO and A2C entry points of each head (a2c: no ratio / no clipping).
+int launch_categorical(const char* who, int a2c, const float* logits, long long B, long long A,
+                       const int64_t* actions, const float* old_logp, const float* adv,
+                       const float* values, const float* vtarg, const float* vold, int has_clip,
+                       double clip, double vcoef, double ecoef, float* loss, float* dlogits,
+                       float* dvalues, float* stats, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  int rc = check_common(who, B, logits, old_logp, adv, values, vtarg, vold, dvalues, loss, stats,
+                        workspace, workspace_bytes, a2c, has_clip);
+  if (rc != DERL_OK) return rc;
+  if (logits != nullptr) {
+    DERL_REQUIRE(A >= 1 && A <= 1024, "%s: A=%lld outside [1, 1024]", who, A);
+    DERL_REQUIRE(actions && dlogits, "%s: actions/dlogits are NULL", who);
+  } else {
+    DERL_REQUIRE(dlogits == nullptr, "%s: dlogits given without logits", who);
+    A = 1;
+  }
+  if ((rc = require_device()) != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  size_t smem = 0;
+  const int R = pick_rows(A, 1, &smem);
+  if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_categorical_kernel),
+                                kMaxTileBytes)) != DERL_OK)
+    return rc;
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
+      logits, (int)A, reinterpret_cast<const long long*>(actions), old_logp, adv, values, vtarg,
+      vold, make_scalars(B, has_clip, clip, vcoef, ecoef, a2c), loss, dlogits, dvalues, stats,
+      workspace);
+  DERL_LAUNCH_CHECK("ppo_loss_categorical_kernel");
+  return DERL_OK;
+}
+
+int launch_gaussian(const char* who, int a2c, const float* loc, const float* scale, long long B,
+                    long long D, const float* actions, const float* old_logp, const float* adv,
+                    const float* values, const float* vtarg, const float* vold, int has_clip,
+                    double clip, double vcoef, double ecoef, float* loss, float* dloc,
+                    float* dscale, float* dvalues, float* stats, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  int rc = check_common(who, B, loc, old_logp, adv, values, vtarg, vold, dvalues, loss, stats,
+                        workspace, workspace_bytes, a2c, has_clip);
+  if (rc != DERL_OK) return rc;
+  if (loc != nullptr) {
+    DERL_REQUIRE(D >= 1 && D <= 256, "%s: D=%lld outside [1, 256]", who, D);
+    DERL_REQUIRE(scale && actions && dloc && dscale, "%s: scale/actions/dloc/dscale are NULL", who);
+  } else {
+    DERL_REQUIRE(dloc == nullptr && dscale == nullptr, "%s: gradients given without loc", who);
+    D = 1;
+  }
+  if ((rc = require_device()) != DERL_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  size_t smem = 0;
+  const int R = pick_rows(D, 3, &smem);
+  if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_gaussian_kernel),
+                                kMaxTileBytes)) != DERL_OK)
+    return rc;
+  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
+  ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
+      loc, scale, (int)D, actions, old_logp, adv, values, vtarg, vold,
+      make_scalars(B, has_clip, clip, vcoef, ecoef, a2c), loss, dloc, dscale, dvalues, stats,
+      workspace);
+  DERL_LAUNCH_CHECK("ppo_loss_gaussian_kernel");
+  return DERL_OK;
+}
+
 }  // namespace
+
 
 LossScalars make_scalars(long long B, int has_clip, double clip, double vcoef, double ecoef,
                          int a2c) {
@@ -261,62 +327,20 @@ int derl_b200_ppo_loss_categorical(const float* logits, int64_t B, int64_t A,
                                    double ecoef, float* loss, float* dlogits, float* dvalues,
                                    float* stats, void* workspace, size_t workspace_bytes,
                                    void* stream) {
-  int rc = check_common("ppo_loss_categorical", B, logits, old_logp, adv, values, vtarg, vold,
-                        dvalues, loss, stats, workspace, workspace_bytes);
-  if (rc != DERL_OK) return rc;
-  if (logits != nullptr) {
-    DERL_REQUIRE(A >= 1 && A <= 1024, "ppo_loss_categorical: A=%lld outside [1, 1024]",
-                 (long long)A);
-    DERL_REQUIRE(actions && dlogits, "ppo_loss_categorical: actions/dlogits are NULL");
-  } else {
-    DERL_REQUIRE(dlogits == nullptr, "ppo_loss_categorical: dlogits given without logits");
-    A = 1;
-  }
-  if ((rc = require_device()) != DERL_OK) return rc;
-  cudaStream_t st = as_stream(stream);
-  size_t smem = 0;
-  const int R = pick_rows(A, 1, &smem);
-  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_categorical_kernel), kMaxTileBytes)) return rc_attr;
-  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
-  ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
-      logits, (int)A, reinterpret_cast<const long long*>(actions), old_logp, adv, values, vtarg,
-      vold, make_scalars(B, has_clip, clip, vcoef, ecoef), loss, dlogits, dvalues, stats,
-      workspace);
-  DERL_LAUNCH_CHECK("ppo_loss_categorical_kernel");
-  return DERL_OK;
+  return launch_categorical("ppo_loss_categorical", 0, logits, B, A, actions, old_logp, adv, values,
+                            vtarg, vold, has_clip, clip, vcoef, ecoef, loss, dlogits, dvalues, stats,
+                            workspace, workspace_bytes, stream);
 }
 
 int derl_b200_ppo_loss_gaussian(const float* loc, const float* scale, int64_t B, int64_t D,
                                 const float* actions, const float* old_logp, const float* adv,
                                 const float* values, const float* vtarg, const float* vold,
-                                int has_clip, double clip, double vcoef, double ecoef,
-                                float* loss, float* dloc, float* dscale, float* dvalues,
-                                float* stats, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-  int rc = check_common("ppo_loss_gaussian", B, loc, old_logp, adv, values, vtarg, vold, dvalues,
-                        loss, stats, workspace, workspace_bytes);
-  if (rc != DERL_OK) return rc;
-  if (loc != nullptr) {
-    DERL_REQUIRE(D >= 1 && D <= 256, "ppo_loss_gaussian: D=%lld outside [1, 256]", (long long)D);
-    DERL_REQUIRE(scale && actions && dloc && dscale,
-                 "ppo_loss_gaussian: scale/actions/dloc/dscale are NULL");
-  } else {
-    DERL_REQUIRE(dloc == nullptr && dscale == nullptr,
-                 "ppo_loss_gaussian: gradients given without loc");
-    D = 1;
-  }
-  if ((rc = require_device()) != DERL_OK) return rc;
-  cudaStream_t st = as_stream(stream);
-  size_t smem = 0;
-  const int R = pick_rows(D, 3, &smem);
-  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_gaussian_kernel), kMaxTileBytes)) return rc_attr;
-  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
-  ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
-      loc, scale, (int)D, actions, old_logp, adv, values, vtarg, vold,
-      make_scalars(B, has_clip, clip, vcoef, ecoef), loss, dloc, dscale, dvalues, stats,
-      workspace);
-  DERL_LAUNCH_CHECK("ppo_loss_gaussian_kernel");
-  return DERL_OK;
+                                int has_clip, double clip, double vcoef, double ecoef, float* loss,
+                                float* dloc, float* dscale, float* dvalues, float* stats,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_gaussian("ppo_loss_gaussian", 0, loc, scale, B, D, actions, old_logp, adv, values,
+                         vtarg, vold, has_clip, clip, vcoef, ecoef, loss, dloc, dscale, dvalues,
+                         stats, workspace, workspace_bytes, stream);
 }
 
 /* Advantage actor-critic loss (derl/alg/a2c.py:19-79) on the same kernels: policy term
@@ -326,28 +350,9 @@ int derl_b200_a2c_loss_categorical(const float* logits, int64_t B, int64_t A,
                                    const float* vtarg, double vcoef, double ecoef, float* loss,
                                    float* dlogits, float* dvalues, float* stats, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  int rc = check_common("a2c_loss_categorical", B, logits, nullptr, adv, values, vtarg, nullptr,
-                        dvalues, loss, stats, workspace, workspace_bytes, 1, 0);
-  if (rc != DERL_OK) return rc;
-  if (logits != nullptr) {
-    DERL_REQUIRE(A >= 1 && A <= 1024, "a2c_loss_categorical: A=%lld outside [1, 1024]",
-                 (long long)A);
-    DERL_REQUIRE(actions && dlogits, "a2c_loss_categorical: actions/dlogits are NULL");
-  } else {
-    DERL_REQUIRE(dlogits == nullptr, "a2c_loss_categorical: dlogits given without logits");
-    A = 1;
-  }
-  if ((rc = require_device()) != DERL_OK) return rc;
-  cudaStream_t st = as_stream(stream);
-  size_t smem = 0;
-  const int R = pick_rows(A, 1, &smem);
-  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_categorical_kernel), kMaxTileBytes)) return rc_attr;
-  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
-  ppo_loss_categorical_kernel<<<loss_grid(B, R), R, smem, st>>>(
-      logits, (int)A, reinterpret_cast<const long long*>(actions), nullptr, adv, values, vtarg,
-      nullptr, make_scalars(B, 0, 0.0, vcoef, ecoef, 1), loss, dlogits, dvalues, stats, workspace);
-  DERL_LAUNCH_CHECK("ppo_loss_categorical_kernel");
-  return DERL_OK;
+  return launch_categorical("a2c_loss_categorical", 1, logits, B, A, actions, nullptr, adv, values,
+                            vtarg, nullptr, 0, 0.0, vcoef, ecoef, loss, dlogits, dvalues, stats,
+                            workspace, workspace_bytes, stream);
 }
 
 int derl_b200_a2c_loss_gaussian(const float* loc, const float* scale, int64_t B, int64_t D,
@@ -355,29 +360,9 @@ int derl_b200_a2c_loss_gaussian(const float* loc, const float* scale, int64_t B,
                                 const float* vtarg, double vcoef, double ecoef, float* loss,
                                 float* dloc, float* dscale, float* dvalues, float* stats,
                                 void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_common("a2c_loss_gaussian", B, loc, nullptr, adv, values, vtarg, nullptr,
-                        dvalues, loss, stats, workspace, workspace_bytes, 1, 0);
-  if (rc != DERL_OK) return rc;
-  if (loc != nullptr) {
-    DERL_REQUIRE(D >= 1 && D <= 256, "a2c_loss_gaussian: D=%lld outside [1, 256]", (long long)D);
-    DERL_REQUIRE(scale && actions && dloc && dscale,
-                 "a2c_loss_gaussian: scale/actions/dloc/dscale are NULL");
-  } else {
-    DERL_REQUIRE(dloc == nullptr && dscale == nullptr,
-                 "a2c_loss_gaussian: gradients given without loc");
-    D = 1;
-  }
-  if ((rc = require_device()) != DERL_OK) return rc;
-  cudaStream_t st = as_stream(stream);
-  size_t smem = 0;
-  const int R = pick_rows(D, 3, &smem);
-  if (int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(ppo_loss_gaussian_kernel), kMaxTileBytes)) return rc_attr;
-  DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
-  ppo_loss_gaussian_kernel<<<loss_grid(B, R), R, smem, st>>>(
-      loc, scale, (int)D, actions, nullptr, adv, values, vtarg, nullptr,
-      make_scalars(B, 0, 0.0, vcoef, ecoef, 1), loss, dloc, dscale, dvalues, stats, workspace);
-  DERL_LAUNCH_CHECK("ppo_loss_gaussian_kernel");
-  return DERL_OK;
+  return launch_gaussian("a2c_loss_gaussian", 1, loc, scale, B, D, actions, nullptr, adv, values,
+                         vtarg, nullptr, 0, 0.0, vcoef, ecoef, loss, dloc, dscale, dvalues, stats,
+                         workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

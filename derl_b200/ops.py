@@ -523,28 +523,7 @@ def _(grad_out, out, unblock=1):
           out.new_empty(chans, dtype=torch.float32))
 
 
-# --------------------------------------------------------------------------- K3: PPO loss
-def _loss_common(head, values, old_log_prob, advantages, value_targets, old_values):
-  ref = head if head is not None else values
-  _need(ref is not None, "ppo_loss: both the policy head and the value head are absent")
-  nb = ref.shape[0]
-  if head is not None:
-    _need(old_log_prob is not None and advantages is not None,
-          "ppo_loss: policy head needs log_prob and advantages")
-    _dense(old_log_prob, "log_prob", (torch.float32,))
-    _dense(advantages, "advantages", (torch.float32,))
-    _need(old_log_prob.numel() == nb and advantages.numel() == nb,
-          "ppo_loss: log_prob / advantages length differs from the batch size")
-  if values is not None:
-    _need(value_targets is not None and old_values is not None,
-          "ppo_loss: value head needs value_targets and old values")
-    for name, t in (("values", values), ("value_targets", value_targets),
-                    ("old values", old_values)):
-      _dense(t, name, (torch.float32,))
-      _need(t.numel() == nb, f"ppo_loss: {name} must have one element per sample")
-  return nb
-
-
+# --------------------------------------------------------------------------- K3: PPO / A2C loss
 def _loss_buffers(ref, nb):
   lib = _lib.load()
   loss = torch.empty((), dtype=torch.float32, device=ref.device)
@@ -552,6 +531,122 @@ def _loss_buffers(ref, nb):
   ws_bytes = lib.derl_b200_ppo_loss_workspace_bytes(nb)
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ref.device)
   return lib, loss, stats, ws, ws_bytes
+
+
+def _check_value_side(who, nb, values, value_targets, old_values, a2c):
+  if values is None:
+    return
+  _need(value_targets is not None and (a2c or old_values is not None),
+        f"{who}: value head needs value_targets" + ("" if a2c else " and old values"))
+  for name, t in (("values", values), ("value_targets", value_targets),
+                  ("old values", old_values)):
+    if t is None:
+      continue
+    _dense(t, name, (torch.float32,))
+    _need(t.numel() == nb, f"{who}: {name} must have one element per sample")
+
+
+def _check_policy_side(who, nb, old_log_prob, advantages, a2c):
+  _need(advantages is not None and (a2c or old_log_prob is not None),
+        f"{who}: policy head needs advantages" + ("" if a2c else " and log_prob"))
+  for name, t in (("log_prob", old_log_prob), ("advantages", advantages)):
+    if t is None:
+      continue
+    _dense(t, name, (torch.float32,))
+    _need(t.numel() == nb, f"{who}: {name} length differs from the batch size")
+
+
+def _grad_like(t, ref):
+  return torch.empty_like(t) if t is not None else ref.new_empty(0)
+
+
+def _run_categorical(a2c, logits, values, actions, old_log_prob, advantages, value_targets,
+                     old_values, cliprange, value_loss_coef, entropy_coef):
+  """Shared body of ppo_loss_categorical / a2c_loss_categorical: one launch of K3."""
+  who = "a2c_loss_categorical" if a2c else "ppo_loss_categorical"
+  ref = logits if logits is not None else values
+  _need(ref is not None, f"{who}: both the policy head and the value head are absent")
+  nb, nact = ref.shape[0], 1
+  if logits is not None:
+    _dense(logits, "logits", (torch.float32,))
+    _need(logits.dim() == 2, f"logits must be [B, A], got {tuple(logits.shape)}")
+    nact = logits.shape[1]
+    _check_policy_side(who, nb, old_log_prob, advantages, a2c)
+    _need(actions is not None, f"{who}: actions missing")
+    _dense(actions, "actions", (torch.int64,))
+    _need(actions.numel() == nb, f"{who}: one action index per sample")
+  _check_value_side(who, nb, values, value_targets, old_values, a2c)
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  dlogits, dvalues = _grad_like(logits, ref), _grad_like(values, ref)
+  with _device_of(ref, who):
+    if a2c:
+      code = lib.derl_b200_a2c_loss_categorical(
+          _p(logits), nb, nact, _p(actions), _p(advantages), _p(values), _p(value_targets),
+          float(value_loss_coef), float(entropy_coef), _p(loss), _p(dlogits), _p(dvalues),
+          _p(stats), _p(ws), ws_bytes, _stream(ref))
+    else:
+      code = lib.derl_b200_ppo_loss_categorical(
+          _p(logits), nb, nact, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
+          _p(value_targets), _p(old_values), int(cliprange is not None),
+          float(cliprange or 0.), float(value_loss_coef), float(entropy_coef), _p(loss),
+          _p(dlogits), _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref))
+    _lib.check(code, who)
+  return loss, dlogits, dvalues, stats
+
+
+def _run_gaussian(a2c, loc, scale, values, actions, old_log_prob, advantages, value_targets,
+                  old_values, cliprange, value_loss_coef, entropy_coef):
+  """Shared body of ppo_loss_gaussian / a2c_loss_gaussian."""
+  who = "a2c_loss_gaussian" if a2c else "ppo_loss_gaussian"
+  ref = loc if loc is not None else values
+  _need(ref is not None, f"{who}: both the policy head and the value head are absent")
+  nb, ndim = ref.shape[0], 1
+  if loc is not None:
+    _need(scale is not None and actions is not None, f"{who}: scale/actions missing")
+    for name, t in (("loc", loc), ("scale", scale), ("actions", actions)):
+      _dense(t, name, (torch.float32,))
+    _need(loc.dim() == 2 and scale.shape == loc.shape and actions.shape == loc.shape,
+          f"loc {tuple(loc.shape)}, scale {tuple(scale.shape)} and actions "
+          f"{tuple(actions.shape)} must all be [B, D]")
+    ndim = loc.shape[1]
+    _check_policy_side(who, nb, old_log_prob, advantages, a2c)
+  _check_value_side(who, nb, values, value_targets, old_values, a2c)
+  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
+  dloc = _grad_like(loc, ref)
+  dscale = _grad_like(scale if loc is not None else None, ref)
+  dvalues = _grad_like(values, ref)
+  with _device_of(ref, who):
+    if a2c:
+      code = lib.derl_b200_a2c_loss_gaussian(
+          _p(loc), _p(scale), nb, ndim, _p(actions), _p(advantages), _p(values),
+          _p(value_targets), float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc),
+          _p(dscale), _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref))
+    else:
+      code = lib.derl_b200_ppo_loss_gaussian(
+          _p(loc), _p(scale), nb, ndim, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
+          _p(value_targets), _p(old_values), int(cliprange is not None), float(cliprange or 0.),
+          float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc), _p(dscale),
+          _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref))
+    _lib.check(code, who)
+  return loss, dloc, dscale, dvalues, stats
+
+
+def _scaled_backward(ngrads, nrest, has_of):
+  """autograd of a loss op: the kernel already produced d loss / d head; scale by grad(loss).
+  ngrads saved gradient tensors, nrest non-differentiable trailing inputs; has_of(inputs) says
+  which heads exist (absent heads get None)."""
+  def setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(*output[1:1 + ngrads])
+    ctx.has = has_of(inputs)
+
+  def backward(ctx, g_loss, *unused):
+    rest = (None,) * nrest
+    if g_loss is None:
+      return (None,) * ngrads + rest
+    return tuple((g_loss * d) if present else None
+                 for d, present in zip(ctx.saved_tensors, ctx.has)) + rest
+  return backward, setup
 
 
 @torch.library.custom_op("derl_b200::ppo_loss_categorical", mutates_args=(), device_types="cuda")
@@ -562,54 +657,20 @@ def ppo_loss_categorical(logits: Optional[Tensor], values: Optional[Tensor],
                          value_loss_coef: float,
                          entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
   """(loss [], dloss/dlogits, dloss/dvalues, stats f32[16]); absent heads give empty grads."""
-  nb = _loss_common(logits, values, old_log_prob, advantages, value_targets, old_values)
-  ref = logits if logits is not None else values
-  nact = 1
-  if logits is not None:
-    _dense(logits, "logits", (torch.float32,))
-    _need(logits.dim() == 2, f"logits must be [B, A], got {tuple(logits.shape)}")
-    nact = logits.shape[1]
-    _need(actions is not None, "ppo_loss_categorical: actions missing")
-    _dense(actions, "actions", (torch.int64,))
-    _need(actions.numel() == nb, "ppo_loss_categorical: one action index per sample")
-  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
-  dlogits = torch.empty_like(logits) if logits is not None else ref.new_empty(0)
-  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
-  with _device_of(ref, "ppo_loss_categorical"):
-    _lib.check(lib.derl_b200_ppo_loss_categorical(
-        _p(logits), nb, nact, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
-        _p(value_targets), _p(old_values), int(cliprange is not None),
-        float(cliprange or 0.), float(value_loss_coef), float(entropy_coef), _p(loss),
-        _p(dlogits), _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref)),
-        "ppo_loss_categorical")
-  return loss, dlogits, dvalues, stats
+  return _run_categorical(False, logits, values, actions, old_log_prob, advantages,
+                          value_targets, old_values, cliprange, value_loss_coef, entropy_coef)
 
 
 @ppo_loss_categorical.register_fake
 def _(logits, values, actions, old_log_prob, advantages, value_targets, old_values, cliprange,
       value_loss_coef, entropy_coef):
   ref = logits if logits is not None else values
-  return (ref.new_empty(()), torch.empty_like(logits) if logits is not None else ref.new_empty(0),
-          torch.empty_like(values) if values is not None else ref.new_empty(0),
-          ref.new_empty(_lib.LOSS_STATS))
+  return ref.new_empty(()), _grad_like(logits, ref), _grad_like(values, ref), \
+      ref.new_empty(_lib.LOSS_STATS)
 
 
-def _cat_setup(ctx, inputs, output):
-  ctx.set_materialize_grads(False)
-  ctx.save_for_backward(output[1], output[2])
-  ctx.has = (inputs[0] is not None, inputs[1] is not None)
-
-
-def _cat_backward(ctx, g_loss, g_dlogits, g_dvalues, g_stats):
-  dlogits, dvalues = ctx.saved_tensors
-  none8 = (None,) * 8
-  if g_loss is None:
-    return (None, None) + none8
-  return ((g_loss * dlogits) if ctx.has[0] else None,
-          (g_loss * dvalues) if ctx.has[1] else None) + none8
-
-
-ppo_loss_categorical.register_autograd(_cat_backward, setup_context=_cat_setup)
+_bw, _su = _scaled_backward(2, 8, lambda i: (i[0] is not None, i[1] is not None))
+ppo_loss_categorical.register_autograd(_bw, setup_context=_su)
 
 
 @torch.library.custom_op("derl_b200::ppo_loss_gaussian", mutates_args=(), device_types="cuda")
@@ -620,113 +681,41 @@ def ppo_loss_gaussian(loc: Optional[Tensor], scale: Optional[Tensor], values: Op
                       value_loss_coef: float,
                       entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
   """(loss [], dloss/dloc, dloss/dscale, dloss/dvalues, stats f32[16])."""
-  nb = _loss_common(loc, values, old_log_prob, advantages, value_targets, old_values)
-  ref = loc if loc is not None else values
-  ndim = 1
-  if loc is not None:
-    _need(scale is not None and actions is not None, "ppo_loss_gaussian: scale/actions missing")
-    for name, t in (("loc", loc), ("scale", scale), ("actions", actions)):
-      _dense(t, name, (torch.float32,))
-    _need(loc.dim() == 2 and scale.shape == loc.shape and actions.shape == loc.shape,
-          f"loc {tuple(loc.shape)}, scale {tuple(scale.shape)} and actions "
-          f"{tuple(actions.shape)} must all be [B, D]")
-    ndim = loc.shape[1]
-  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
-  dloc = torch.empty_like(loc) if loc is not None else ref.new_empty(0)
-  dscale = torch.empty_like(scale) if loc is not None else ref.new_empty(0)
-  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
-  with _device_of(ref, "ppo_loss_gaussian"):
-    _lib.check(lib.derl_b200_ppo_loss_gaussian(
-        _p(loc), _p(scale), nb, ndim, _p(actions), _p(old_log_prob), _p(advantages), _p(values),
-        _p(value_targets), _p(old_values), int(cliprange is not None), float(cliprange or 0.),
-        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc), _p(dscale),
-        _p(dvalues), _p(stats), _p(ws), ws_bytes, _stream(ref)), "ppo_loss_gaussian")
-  return loss, dloc, dscale, dvalues, stats
+  return _run_gaussian(False, loc, scale, values, actions, old_log_prob, advantages,
+                       value_targets, old_values, cliprange, value_loss_coef, entropy_coef)
 
 
 @ppo_loss_gaussian.register_fake
 def _(loc, scale, values, actions, old_log_prob, advantages, value_targets, old_values,
       cliprange, value_loss_coef, entropy_coef):
   ref = loc if loc is not None else values
-  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
-  return ref.new_empty(()), grad(loc), grad(scale), grad(values), ref.new_empty(_lib.LOSS_STATS)
+  return (ref.new_empty(()), _grad_like(loc, ref), _grad_like(scale, ref),
+          _grad_like(values, ref), ref.new_empty(_lib.LOSS_STATS))
 
 
-def _gauss_setup(ctx, inputs, output):
-  ctx.set_materialize_grads(False)
-  ctx.save_for_backward(output[1], output[2], output[3])
-  ctx.has = (inputs[0] is not None, inputs[2] is not None)
+_bw, _su = _scaled_backward(3, 8, lambda i: (i[0] is not None, i[0] is not None, i[2] is not None))
+ppo_loss_gaussian.register_autograd(_bw, setup_context=_su)
 
 
-def _gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
-  dloc, dscale, dvalues = ctx.saved_tensors
-  none8 = (None,) * 8
-  if g_loss is None:
-    return (None, None, None) + none8
-  return ((g_loss * dloc) if ctx.has[0] else None, (g_loss * dscale) if ctx.has[0] else None,
-          (g_loss * dvalues) if ctx.has[1] else None) + none8
-
-
-ppo_loss_gaussian.register_autograd(_gauss_backward, setup_context=_gauss_setup)
-
-
-# --------------------------------------------------------------------------- A2C loss
 @torch.library.custom_op("derl_b200::a2c_loss_categorical", mutates_args=(), device_types="cuda")
 def a2c_loss_categorical(logits: Optional[Tensor], values: Optional[Tensor],
                          actions: Optional[Tensor], advantages: Optional[Tensor],
                          value_targets: Optional[Tensor], value_loss_coef: float,
                          entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
   """Advantage actor-critic loss (categorical head): (loss [], dlogits, dvalues, stats f32[16])."""
-  ref = logits if logits is not None else values
-  _need(ref is not None, "a2c_loss: both heads are absent")
-  nb, nact = ref.shape[0], 1
-  if logits is not None:
-    _dense(logits, "logits", (torch.float32,))
-    _need(logits.dim() == 2 and actions is not None and advantages is not None,
-          "a2c_loss_categorical: logits must be [B, A] with actions and advantages")
-    _dense(actions, "actions", (torch.int64,))
-    _dense(advantages, "advantages", (torch.float32,))
-    _need(actions.numel() == nb and advantages.numel() == nb, "one action / advantage per sample")
-    nact = logits.shape[1]
-  if values is not None:
-    _need(value_targets is not None, "a2c_loss: value head needs value_targets")
-    _dense(values, "values", (torch.float32,))
-    _dense(value_targets, "value_targets", (torch.float32,))
-    _need(values.numel() == nb and value_targets.numel() == nb, "one value / target per sample")
-  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
-  dlogits = torch.empty_like(logits) if logits is not None else ref.new_empty(0)
-  dvalues = torch.empty_like(values) if values is not None else ref.new_empty(0)
-  with _device_of(ref, "a2c_loss_categorical"):
-    _lib.check(lib.derl_b200_a2c_loss_categorical(
-        _p(logits), nb, nact, _p(actions), _p(advantages), _p(values), _p(value_targets),
-        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dlogits), _p(dvalues),
-        _p(stats), _p(ws), ws_bytes, _stream(ref)), "a2c_loss_categorical")
-  return loss, dlogits, dvalues, stats
+  return _run_categorical(True, logits, values, actions, None, advantages, value_targets, None,
+                          None, value_loss_coef, entropy_coef)
 
 
 @a2c_loss_categorical.register_fake
 def _(logits, values, actions, advantages, value_targets, value_loss_coef, entropy_coef):
   ref = logits if logits is not None else values
-  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
-  return ref.new_empty(()), grad(logits), grad(values), ref.new_empty(_lib.LOSS_STATS)
+  return ref.new_empty(()), _grad_like(logits, ref), _grad_like(values, ref), \
+      ref.new_empty(_lib.LOSS_STATS)
 
 
-def _a2c_cat_setup(ctx, inputs, output):
-  ctx.set_materialize_grads(False)
-  ctx.save_for_backward(output[1], output[2])
-  ctx.has = (inputs[0] is not None, inputs[1] is not None)
-
-
-def _a2c_cat_backward(ctx, g_loss, g_dlogits, g_dvalues, g_stats):
-  dlogits, dvalues = ctx.saved_tensors
-  rest = (None,) * 5
-  if g_loss is None:
-    return (None, None) + rest
-  return ((g_loss * dlogits) if ctx.has[0] else None,
-          (g_loss * dvalues) if ctx.has[1] else None) + rest
-
-
-a2c_loss_categorical.register_autograd(_a2c_cat_backward, setup_context=_a2c_cat_setup)
+_bw, _su = _scaled_backward(2, 5, lambda i: (i[0] is not None, i[1] is not None))
+a2c_loss_categorical.register_autograd(_bw, setup_context=_su)
 
 
 @torch.library.custom_op("derl_b200::a2c_loss_gaussian", mutates_args=(), device_types="cuda")
@@ -735,57 +724,19 @@ def a2c_loss_gaussian(loc: Optional[Tensor], scale: Optional[Tensor], values: Op
                       value_targets: Optional[Tensor], value_loss_coef: float,
                       entropy_coef: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
   """Advantage actor-critic loss (diagonal-Gaussian head)."""
-  ref = loc if loc is not None else values
-  _need(ref is not None, "a2c_loss: both heads are absent")
-  nb, ndim = ref.shape[0], 1
-  if loc is not None:
-    _need(scale is not None and actions is not None and advantages is not None,
-          "a2c_loss_gaussian: scale / actions / advantages missing")
-    for name, t in (("loc", loc), ("scale", scale), ("actions", actions),
-                    ("advantages", advantages)):
-      _dense(t, name, (torch.float32,))
-    _need(loc.dim() == 2 and scale.shape == loc.shape and actions.shape == loc.shape
-          and advantages.numel() == nb, "loc, scale, actions must be [B, D]; one advantage per row")
-    ndim = loc.shape[1]
-  if values is not None:
-    _need(value_targets is not None, "a2c_loss: value head needs value_targets")
-    _dense(values, "values", (torch.float32,))
-    _dense(value_targets, "value_targets", (torch.float32,))
-    _need(values.numel() == nb and value_targets.numel() == nb, "one value / target per sample")
-  lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
-  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
-  dloc, dscale, dvalues = grad(loc), grad(scale if loc is not None else None), grad(values)
-  with _device_of(ref, "a2c_loss_gaussian"):
-    _lib.check(lib.derl_b200_a2c_loss_gaussian(
-        _p(loc), _p(scale), nb, ndim, _p(actions), _p(advantages), _p(values), _p(value_targets),
-        float(value_loss_coef), float(entropy_coef), _p(loss), _p(dloc), _p(dscale), _p(dvalues),
-        _p(stats), _p(ws), ws_bytes, _stream(ref)), "a2c_loss_gaussian")
-  return loss, dloc, dscale, dvalues, stats
+  return _run_gaussian(True, loc, scale, values, actions, None, advantages, value_targets, None,
+                       None, value_loss_coef, entropy_coef)
 
 
 @a2c_loss_gaussian.register_fake
 def _(loc, scale, values, actions, advantages, value_targets, value_loss_coef, entropy_coef):
   ref = loc if loc is not None else values
-  grad = lambda t: torch.empty_like(t) if t is not None else ref.new_empty(0)
-  return ref.new_empty(()), grad(loc), grad(scale), grad(values), ref.new_empty(_lib.LOSS_STATS)
+  return (ref.new_empty(()), _grad_like(loc, ref), _grad_like(scale, ref),
+          _grad_like(values, ref), ref.new_empty(_lib.LOSS_STATS))
 
 
-def _a2c_gauss_setup(ctx, inputs, output):
-  ctx.set_materialize_grads(False)
-  ctx.save_for_backward(output[1], output[2], output[3])
-  ctx.has = (inputs[0] is not None, inputs[2] is not None)
-
-
-def _a2c_gauss_backward(ctx, g_loss, g_dloc, g_dscale, g_dvalues, g_stats):
-  dloc, dscale, dvalues = ctx.saved_tensors
-  rest = (None,) * 5
-  if g_loss is None:
-    return (None, None, None) + rest
-  return ((g_loss * dloc) if ctx.has[0] else None, (g_loss * dscale) if ctx.has[0] else None,
-          (g_loss * dvalues) if ctx.has[1] else None) + rest
-
-
-a2c_loss_gaussian.register_autograd(_a2c_gauss_backward, setup_context=_a2c_gauss_setup)
+_bw, _su = _scaled_backward(3, 5, lambda i: (i[0] is not None, i[0] is not None, i[2] is not None))
+a2c_loss_gaussian.register_autograd(_bw, setup_context=_su)
 
 
 # --------------------------------------------------------------------------- K8: MLP PPO update

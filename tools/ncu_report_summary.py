@@ -1,6 +1,6 @@
 """Summarise an `ncu --set full` report (read here, no GPU needed) into a table and a traffic JSON:
 
-  python tools/ncu_report_summary.py gpurun_out/kernels.ncu-rep profiles/r02_kernels_ncu.txt \\
+  python tools/ncu_report_summary.py gpurun_out/kernels.ncu-rep|raw.csv profiles/r02_kernels_ncu.txt \\
          profiles/r02_kernel_traffic.json
 
 One row per (kernel, grid): the LAST captured launch of each — duration, DRAM bytes read / written,
@@ -32,8 +32,11 @@ SCALE = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "ns
 
 def main():
   rep, table_path, json_path = sys.argv[1:4]
-  raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                       text=True, check=True).stdout
+  if rep.endswith(".csv"):   # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv
+    raw = open(rep).read()
+  else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                         text=True, check=True).stdout
   rows = list(csv.reader(io.StringIO(raw)))
   hdr, units = rows[0], rows[1]
   col = {h: i for i, h in enumerate(hdr)}
