@@ -11,7 +11,8 @@
 // of 64 rows and 11 k parameters none of that is bandwidth or FLOP work: the eager path spends
 // 1.6 ms per optimiser step on launches and Python, a CUDA-graph replay 0.25 ms.  Here the
 // whole update is one persistent CTA: parameters and their gradients live in shared memory for
-// all 320 steps (odd row pitches make every GEMM operand access conflict-free), a step is
+// all 320 steps (row pitch 68 floats: 16-byte aligned rows whose float4 loads spread over all
+// bank groups), a step is
 // ~30 k cycles of fp32 FMA work, and Adam's moment vectors are the only per-step global traffic
 // (88 KB, L2-resident, kept in the same padded layout as the shared parameter block so that the
 // update loop is one division-free sweep with independent loads).  fp32 FMA on CUDA cores, not tensor cores: the contract is the
@@ -19,9 +20,11 @@
 // latency-, not throughput-bound.
 //
 // Thread roles: 512 threads; threads 0-255 work on the policy network, 256-511 on the value
-// network.  A [64 x 64] GEMM is 256 threads x (4 x 4) register tile, rows tm + 16 i, columns
-// tn + 16 j (tm = t / 16, tn = t % 16), so that a warp reads 2 distinct A and 16 consecutive B
-// addresses per step of the reduction.
+// network.  A [64 x 64 x 64] GEMM is 256 threads x (4 x 4) register tile with float4 operand
+// loads — along the reduction index where both operands are contiguous in it (forward),
+// along the tile otherwise (dgrad, wgrad): 8 LDS.128 per 64 FMA.  The first profile (ncu:
+// `not_selected` and `barrier` on top, i.e. issue-bound on one SM) had 8 scalar LDS + 8 address
+// IMADs per 16 FMA and a full 64 x 64 tile for the [64 x obs] weight gradient.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -31,7 +34,7 @@ namespace derl {
 namespace {
 
 constexpr int kH = 64;          // hidden width of both MLPs
-constexpr int kHP = kH + 1;     // odd pitch of a [*, 64] array in shared memory
+constexpr int kHP = kH + 4;     // pitch of a [*, 64] array in shared memory: 16-byte aligned rows
 constexpr int kRows = 64;       // rows per pass (a larger minibatch accumulates over passes)
 constexpr int kThreads = 512;
 constexpr int kNet = 256;       // threads per network
@@ -47,14 +50,14 @@ struct MlpTensor {
 
 // Shared-memory plan, identical on host and device (float offsets unless noted).
 struct Carve {
-  int OP, DP;                   // odd pitches of [*, obs] and [*, act] arrays
+  int OP, DP;                   // pitches of [*, obs] (multiple of 4, zero padded) and [*, act] (odd)
   int params;                   // floats of one parameter block (W or G)
   int off_w, off_g, off_x, off_h[2][3], off_adv, off_oldlp, off_vt, off_vold, off_act, off_loc,
       off_val, off_dloc, off_dscale, off_dval, off_sd, off_misc, off_idx, off_red, total;
   int t_off[kTensors], t_pitch[kTensors], t_rows[kTensors], t_cols[kTensors];
 
   __host__ __device__ Carve(int O, int D) {
-    OP = O | 1;
+    OP = (O + 3) & ~3;
     DP = D | 1;
     int o = 0;
     for (int net = 0; net < 2; ++net) {
@@ -68,7 +71,7 @@ struct Carve {
         t_pitch[t] = pitch[i];
         t_rows[t] = rows[i];
         t_cols[t] = cols[i];
-        o += rows[i] * pitch[i];
+        o += (rows[i] * pitch[i] + 3) & ~3;     // every tensor starts 16-byte aligned
       }
     }
     t_off[12] = o;
@@ -93,6 +96,7 @@ struct Carve {
     off_loc = o; o += kRows * DP;
     off_dloc = o; o += kRows * DP;
     off_dscale = o; o += kRows * DP;
+    o = (o + 3) & ~3;
     off_sd = o; o += kMaxAct;
     off_misc = o; o += 16;                       // mean, denom, clip coefficient, Adam scalars
     o = (o + 1) & ~1;
@@ -118,44 +122,111 @@ struct MlpArgs {
   float* ws_v;     // element e of the workspace belongs to element e of the parameter block
 };
 
-// C(m, n) = sum_r A(r, m) * B(r, n) for m < M <= 64, n < N <= 64, by the 256 threads of one net.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// The three GEMM shapes of a 64-row pass, each by the 256 threads of one net (t = 0..255,
+// tm = t / 16, tn = t % 16), 4 x 4 outputs per thread, operands read as float4.
+//
+// kk: C(m, n) = sum_k A[m][k] B[n][k], both operands contiguous along the reduction index
+//     (forward layers: activations [row][k], weights [unit][k]).  m = tm + 16 i, n = tn + 16 j:
+//     a warp reads 2 distinct A chunks and 16 B chunks in 8 distinct bank groups.  K % 4 == 0.
 template <typename Epi>
-__device__ __forceinline__ void gemm64(const float* __restrict__ A, int a_sr, int a_sm, int M,
-                                       const float* __restrict__ B, int b_sr, int b_sn, int N,
-                                       int R, int t, Epi epi) {
+__device__ __forceinline__ void gemm_kk(const float* __restrict__ A, int a_p,
+                                        const float* __restrict__ B, int b_p, int K, int t,
+                                        Epi epi) {
   const int tm = t >> 4, tn = t & 15;
-  int am[4], bn[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = tm + 16 * i, n = tn + 16 * i;
-    am[i] = (m < M ? m : 0) * a_sm;
-    bn[i] = (n < N ? n : 0) * b_sn;
-  }
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < R; ++r) {
-    float a[4], b[4];
+  const float* a0 = A + tm * a_p;
+  const float* b0 = B + tn * b_p;
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float4 a[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a[i] = A[r * a_sr + am[i]];
-      b[i] = B[r * b_sr + bn[i]];
+      a[i] = ld4(a0 + 16 * i * a_p + k);
+      b[i] = ld4(b0 + 16 * i * b_p + k);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = tm + 16 * i, n = tn + 16 * j;
-      if (m < M && n < N) epi(m, n, acc[i][j]);
+    for (int j = 0; j < 4; ++j) epi(tm + 16 * i, tn + 16 * j, acc[i][j]);
+}
+
+// kn: C(m, n) = sum_r A[m][r] B[r][n]: A contiguous along the reduction, B along the tile
+//     (dgrad: dZ [row][unit] x W [unit][k]).  m = tm + 16 i, n = 4 tn .. 4 tn + 3.  R % 4 == 0.
+template <typename Epi>
+__device__ __forceinline__ void gemm_kn(const float* __restrict__ A, int a_p,
+                                        const float* __restrict__ B, int b_p, int R, int t,
+                                        Epi epi) {
+  const int tm = t >> 4, tn = t & 15;
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* a0 = A + tm * a_p;
+  const float* b0 = B + 4 * tn;
+#pragma unroll 2
+  for (int r = 0; r < R; r += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = ld4(a0 + 16 * i * a_p + r);
+      b[i] = ld4(b0 + (r + i) * b_p);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float ar[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[i].x = fmaf(ar[e], b[e].x, acc[i].x);
+        acc[i].y = fmaf(ar[e], b[e].y, acc[i].y);
+        acc[i].z = fmaf(ar[e], b[e].z, acc[i].z);
+        acc[i].w = fmaf(ar[e], b[e].w, acc[i].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi(tm + 16 * i, 4 * tn, acc[i]);
+}
+
+// nn: C(m, n) += sum_r A[r][m] B[r][n] over rows [r0, r1): both operands contiguous along the
+//     tile (weight gradients: dZ [row][unit] x activations [row][k]).  m = 4 tm .., n = 4 tn ..
+template <typename Epi>
+__device__ __forceinline__ void gemm_nn(const float* __restrict__ A, int a_p,
+                                        const float* __restrict__ B, int b_p, int r0, int r1,
+                                        int tm, int tn, Epi epi) {
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* a0 = A + 4 * tm;
+  const float* b0 = B + 4 * tn;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const float4 a = ld4(a0 + r * a_p), b = ld4(b0 + r * b_p);
+    const float ar[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[i].x = fmaf(ar[i], b.x, acc[i].x);
+      acc[i].y = fmaf(ar[i], b.y, acc[i].y);
+      acc[i].z = fmaf(ar[i], b.z, acc[i].z);
+      acc[i].w = fmaf(ar[i], b.w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi(4 * tm + i, 4 * tn, acc[i]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpArgs a) {
@@ -219,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
   const float kLogSqrt2Pi = 0.918938533204672742f;
   const float kHalfLog2PiE = 1.418938533204672742f;
 
+  double pow1 = pow(a.beta1, (double)a.step0), pow2 = pow(a.beta2, (double)a.step0);
   for (int step = 0; step < a.nsteps; ++step) {
     const int epoch = step / a.nmb, j = step - epoch * a.nmb;
     const long long start = (long long)j * a.mb;
@@ -281,10 +353,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
         s_vold[tid] = vo;
       }
       __syncthreads();
-      for (int e = tid; e < kRows * O; e += kThreads) {
-        const int r = e / O, k = e - r * O;
+      for (int e = tid; e < kRows * OP; e += kThreads) {   // padding columns k >= O are zeros
+        const int r = e / OP, k = e - r * OP;
         float x = 0.f;
-        if (r < rows) {
+        if (r < rows && k < O) {
           const long long g = s_idx[r] * O + k;
           x = a.obs_f64 ? (float)__ldg(reinterpret_cast<const double*>(a.obs) + g)
                         : __ldg(reinterpret_cast<const float*>(a.obs) + g);
@@ -298,11 +370,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
       __syncthreads();
 
       // ---- forward: H1 = tanh(X W1^T + b1), H2 = tanh(H1 W2^T + b2)
-      gemm64(X, 1, OP, kRows, W + oW1, 1, OP, kH, O, t,
-             [&](int m, int n, float v) { H1[m * kHP + n] = tanhf(v + W[ob1 + n]); });
+      gemm_kk(X, OP, W + oW1, OP, OP, t,
+              [&](int m, int n, float v) { H1[m * kHP + n] = tanhf(v + W[ob1 + n]); });
       __syncthreads();
-      gemm64(H1, 1, kHP, kRows, W + oW2, 1, kHP, kH, kH, t,
-             [&](int m, int n, float v) { H2[m * kHP + n] = tanhf(v + W[ob2 + n]); });
+      gemm_kk(H1, kHP, W + oW2, kHP, kH, t,
+              [&](int m, int n, float v) { H2[m * kHP + n] = tanhf(v + W[ob2 + n]); });
       __syncthreads();
       // ---- heads: loc [64, D] from the policy trunk, value [64] from the value trunk
       {
@@ -313,8 +385,14 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
           const float* h = (col < D ? H2p : H2v) + r * kHP;
           const float* w = W + (col < D ? oW3p + col * kHP : oW3v);
           float z = 0.f;
-#pragma unroll 8
-          for (int k = 0; k < kH; ++k) z = fmaf(h[k], w[k], z);
+#pragma unroll 4
+          for (int k = 0; k < kH; k += 4) {
+            const float4 hv = ld4(h + k), wv = ld4(w + k);
+            z = fmaf(hv.x, wv.x, z);
+            z = fmaf(hv.y, wv.y, z);
+            z = fmaf(hv.z, wv.z, z);
+            z = fmaf(hv.w, wv.w, z);
+          }
           if (col < D) s_loc[r * DP + col] = z + W[ob3p + col];
           else s_val[r] = z + W[ob3v];
         }
@@ -401,11 +479,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
       }
       __syncthreads();
       // ---- layer 2: dW2 += dZ2^T H1, db2, dZ1 = (dZ2 W2) * (1 - H1^2) -> Sb
-      gemm64(H2, kHP, 1, kH, H1, kHP, 1, kH, kRows, t,
-             [&](int m, int n, float v) { G[oW2 + m * kHP + n] += v; });
-      gemm64(H2, 1, kHP, kRows, W + oW2, kHP, 1, kH, kH, t, [&](int m, int n, float v) {
-        const float h = H1[m * kHP + n];
-        Sb[m * kHP + n] = v * (1.f - h * h);
+      gemm_nn(H2, kHP, H1, kHP, 0, kRows, t >> 4, t & 15, [&](int m, int n, float4 v) {
+        float4* g = reinterpret_cast<float4*>(G + oW2 + m * kHP + n);
+        float4 cur = *g;
+        cur.x += v.x; cur.y += v.y; cur.z += v.z; cur.w += v.w;
+        *g = cur;
+      });
+      gemm_kn(H2, kHP, W + oW2, kHP, kH, t, [&](int m, int n, float4 v) {
+        const float4 h = ld4(H1 + m * kHP + n);
+        *reinterpret_cast<float4*>(Sb + m * kHP + n) =
+            make_float4(v.x * (1.f - h.x * h.x), v.y * (1.f - h.y * h.y), v.z * (1.f - h.z * h.z),
+                        v.w * (1.f - h.w * h.w));
       });
       if (t < kH) {
         float s = 0.f;
@@ -413,9 +497,24 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
         G[ob2 + t] += s;
       }
       __syncthreads();
-      // ---- layer 1: dW1 += dZ1^T X, db1
-      gemm64(Sb, kHP, 1, kH, X, OP, 1, O, kRows, t,
-             [&](int m, int n, float v) { G[oW1 + m * OP + n] += v; });
+      // ---- layer 1: dW1 += dZ1^T X (only OP / 4 column groups exist: 16 x OP/4 tiles, the 64
+      // rows split over as many thread groups as fit, shared-memory atomics), db1
+      {
+        const int ntn = OP >> 2, tiles = 16 * ntn;
+        const int groups = kNet / tiles > 0 ? kNet / tiles : 1;
+        const int grp = t / tiles, id = t - grp * tiles;
+        if (grp < groups) {
+          const int per = (kRows + groups - 1) / groups;
+          const int r0 = grp * per, r1 = r0 + per < kRows ? r0 + per : kRows;
+          gemm_nn(Sb, kHP, X, OP, r0, r1, id / ntn, id % ntn, [&](int m, int n, float4 v) {
+            float* g = G + oW1 + m * OP + n;
+            atomicAdd(g, v.x);
+            atomicAdd(g + 1, v.y);
+            atomicAdd(g + 2, v.z);
+            atomicAdd(g + 3, v.w);
+          });
+        }
+      }
       if (t < kH) {
         float s = 0.f;
         for (int r = 0; r < kRows; ++r) s += Sb[r * kHP + t];
@@ -444,8 +543,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_mlp_update_kernel(const MlpAr
         const float norm = (float)sqrt(sq[0]);
         coef = fminf((float)a.max_norm / (norm + 1e-6f), 1.f);
       }
-      const double stepno = (double)(a.step0 + step + 1);
-      const double bc1 = 1.0 - pow(a.beta1, stepno), bc2 = 1.0 - pow(a.beta2, stepno);
+      pow1 *= a.beta1;   // beta^(step0 + step + 1), carried from step to step (thread 0)
+      pow2 *= a.beta2;
+      const double bc1 = 1.0 - pow1, bc2 = 1.0 - pow2;
       misc[2] = coef;
       misc[3] = (float)(a.lr / bc1);       // step_size
       misc[4] = (float)sqrt(bc2);          // bias_correction2_sqrt
