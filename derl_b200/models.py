@@ -114,7 +114,9 @@ class _StemConvReLU(torch.autograd.Function):
   def forward(ctx, frames, weight, bias, dtype, out_block, rows=None):
     """rows: int64 indices — the batch is frames[rows], read in place (fused minibatch gather)."""
     mask = None
-    if _StemConvReLU.tensor_memory and dtype == torch.float32 and _StemConvReLU.fused_backward:
+    wants_backward = any(ctx.needs_input_grad[1:3])   # no mask for rollouts / no_grad forwards
+    if (_StemConvReLU.tensor_memory and dtype == torch.float32 and _StemConvReLU.fused_backward
+        and wants_backward):
       out, mask = torch.ops.derl_b200.stem_conv_relu_mask(frames, weight.contiguous(), bias,
                                                           out_block, rows)
     else:

@@ -314,3 +314,29 @@ def test_take_default_axis_selects_envs():
   d.Take([2, 0])(traj)
   assert traj["rewards"].tolist() == [[2., 0.], [5., 3.], [8., 6.], [11., 9.]]
   assert traj["resets"].shape == (4, 2)
+
+
+@pytest.mark.parametrize("kind,nenvs", [("atari", 3), ("mujoco", None)])
+def test_bench_reference_arm_generates_the_same_rollout_without_importing_the_package(kind, nenvs):
+  """bench.py's reference arm must not import derl_b200 (no CUDA library in that process), so it
+  carries its own copy of the seeded host rollout generator: the copy must stay equal to
+  derl_b200.make_rollout(device="cpu") array for array."""
+  import importlib.util
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("_bench_under_test", os.path.join(root, "bench.py"))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  theirs = bench.host_rollout(kind, 5, nenvs, seed=7)
+  ours = d.make_rollout(kind, 5, nenvs, device="cpu", seed=7)
+  assert set(theirs) == set(ours)
+  for key in ours:
+    if key == "state":
+      np.testing.assert_array_equal(theirs[key]["latest_observations"],
+                                    ours[key]["latest_observations"])
+    else:
+      assert theirs[key].dtype == ours[key].dtype, key
+      np.testing.assert_array_equal(theirs[key], ours[key])
+  # and the arm's CPU path runs on it (oracle port here unless the reference tree is present)
+  sec, how = bench.cpu_update_seconds(kind, nenvs, 5, 1, 1, steps=1, warmup=0)
+  assert sec > 0 and how in ("live", "port")
