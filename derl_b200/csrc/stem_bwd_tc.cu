@@ -177,33 +177,40 @@ stem_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_frames, const long lon
     __syncwarp();
   } else if (warp == kWorkers + 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      for (int it = 0; it < nframes; ++it) {
-        const int b = it & 1;
-        const unsigned ph = (unsigned)((it >> 1) & 1);
-        mbar_wait(&tempty[b], ph ^ 1u);
-        mbar_wait(&frame_full[b], ph);
-        mbar_wait(&gq_full[b], ph);
-        tcgen05_fence_after();
-        const uint32_t f_addr = smem_u32(smem + BtSmem::frame + b * kFrameBuf);
-        const uint32_t g_addr = smem_u32(gq + b * kGqBytes);
-#pragma unroll 1
+    // The whole warp runs the control flow (waits, descriptor arithmetic: warp-uniform, so it
+    // lives in uniform registers); one elected lane issues the MMAs and the commits.
+    for (int it = 0; it < nframes; ++it) {
+      const int b = it & 1;
+      const unsigned ph = (unsigned)((it >> 1) & 1);
+      mbar_wait(&tempty[b], ph ^ 1u);
+      mbar_wait(&frame_full[b], ph);
+      mbar_wait(&gq_full[b], ph);
+      tcgen05_fence_after();
+      // Descriptors are built once per frame and advanced by adding to the 14-bit start-address
+      // field (units of 16 B; shared-memory addresses stay below 2^18, so no carry leaves the
+      // field): ~4 instructions per MMA instead of ~14 — with the full descriptor arithmetic per
+      // MMA in a single divergent thread its issue rate, not the tensor pipe, set the frame time
+      // (ncu: workers 34 % of their samples on the accumulator barrier, tensor pipe 32 % active).
+      const uint64_t a_frame = umma_desc(smem_u32(smem + BtSmem::frame + b * kFrameBuf),
+                                         /*lbo: next 8 blocks*/ 128, /*sbo: next 16 taps*/ kPlaneBytes);
+      const uint64_t g_desc = umma_desc(smem_u32(gq + b * kGqBytes), 1024, 128);
+      const uint32_t d0 = tmem + (uint32_t)(b * 256);
+      if (elect_one_sync()) {
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t d = tmem + (uint32_t)(b * 256 + q * 64);
-          const uint32_t a0 = f_addr + (uint32_t)((21 * (q >> 1) + (q & 1)) * 16);
+          const uint64_t a_desc = a_frame + (uint64_t)(21 * (q >> 1) + (q & 1));   // 16 (21a + b) B
 #pragma unroll
           for (int ks = 0; ks < kKSteps; ++ks) {
-            umma_i8(d, umma_desc(a0 + ks * 512, /*lbo: next 8 blocks*/ 128, /*sbo: next 16 taps*/
-                                 kPlaneBytes),
-                    umma_desc(g_addr + ks * 2048, 1024, 128), kIdesc, ks != 0);
+            umma_i8(d0 + q * 64, a_desc + (uint64_t)(ks * 32), g_desc + (uint64_t)(ks * 128), kIdesc,
+                    ks != 0);
           }
         }
         umma_commit(&frame_empty[b]);
         umma_commit(&gq_empty[b]);
         umma_commit(&tfull[b]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================================================================== workers
     const int ch = lane;                       // quantiser role: one channel per lane

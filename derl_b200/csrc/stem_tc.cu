@@ -162,36 +162,39 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t w_addr = smem_u32(wsm);
-      int it = 0;
-      for (long long f = first; f < batch; f += stride, ++it) {
-        const int b = it % kStages, g = it & 1;
-        const unsigned ph = (unsigned)((it >> 1) & 1);
-        mbar_wait(&tempty[g], ph ^ 1u);     // the epilogue has drained this accumulator buffer
-        mbar_wait(&full[b], (unsigned)((it / kStages) & 1));   // the frame has landed
-        tcgen05_fence_after();
-        const uint32_t f_addr = smem_u32(smem + TcSmem::frame + b * kFrameBuf);
-#pragma unroll 1
+    // The whole warp runs the control flow (waits, descriptor arithmetic: warp-uniform); one
+    // elected lane issues the MMAs and the commits.
+    const uint64_t w_desc = umma_desc(smem_u32(wsm), 1024, 128);
+    int it = 0;
+    for (long long f = first; f < batch; f += stride, ++it) {
+      const int b = it % kStages, g = it & 1;
+      const unsigned ph = (unsigned)((it >> 1) & 1);
+      mbar_wait(&tempty[g], ph ^ 1u);     // the epilogue has drained this accumulator buffer
+      mbar_wait(&full[b], (unsigned)((it / kStages) & 1));   // the frame has landed
+      tcgen05_fence_after();
+      // descriptors once per frame, advanced by adding to the start-address field (units of 16 B)
+      const uint64_t a_frame = umma_desc(smem_u32(smem + TcSmem::frame + b * kFrameBuf),
+                                         kPlaneBytes, 128);
+      const uint32_t d0 = tmem + (uint32_t)(g * 256);
+      if (elect_one_sync()) {
+#pragma unroll
         for (int mt = 0; mt < kMTiles; ++mt) {
-          const uint32_t d = tmem + (uint32_t)(g * 256 + mt * 64);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
             for (int ip = 0; ip < 2; ++ip) {
-              const uint32_t a_addr = f_addr + (uint32_t)(2 * ip * kPlaneBytes +
-                                                         (21 * (q >> 1) + (q & 1)) * 16 + mt * 2048);
-              const uint32_t b_addr = w_addr + (uint32_t)((q * 4 + 2 * ip) * 1024);
-              umma_i8(d, umma_desc(a_addr, kPlaneBytes, 128), umma_desc(b_addr, 1024, 128), kIdesc,
-                      (q | ip) != 0);
+              const uint64_t a_desc = a_frame + (uint64_t)((2 * ip * kPlaneBytes +
+                                                            (21 * (q >> 1) + (q & 1)) * 16 + mt * 2048) >> 4);
+              const uint64_t b_desc = w_desc + (uint64_t)(((q * 4 + 2 * ip) * 1024) >> 4);
+              umma_i8(d0 + mt * 64, a_desc, b_desc, kIdesc, (q | ip) != 0);
             }
           }
         }
         umma_commit(&empty[b]);    // frame buffer may be refilled once these MMAs have read it
         umma_commit(&tfull[g]);    // accumulators complete
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================================================================== epilogue groups
     // 16 warps = 2 groups (alternate frames) x 4 tensor-memory lane quarters x 2 tile parities.

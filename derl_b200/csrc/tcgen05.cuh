@@ -53,12 +53,28 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64
       : "memory");
 }
 
+// (with a compile-time `accumulate` the setp folds away when the call site is unrolled)
+
 // mbarrier arrival when every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// One lane of a fully converged warp (the pattern the uniform datapath wants: control flow and
+// descriptor arithmetic stay warp-uniform, only the issue itself is predicated).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tcgen05_fence_before() {

@@ -31,8 +31,10 @@ def _need(cond, msg):
     raise ValueError(msg)
 
 
-# DERL_B200_CHECK_INDICES=1: validate gather indices on the host (one device sync per call).
-# Off by default: the runner wrappers only ever pass permutations they built themselves.
+# DERL_B200_CHECK_INDICES=1: validate gather indices and categorical action indices on the host
+# (one device sync per call).  Off by default: the runner wrappers only ever pass permutations
+# they built themselves, `Take` validates its (host) indices before any launch, and actions come
+# out of the policy's own sampler.
 CHECK_INDICES = os.environ.get("DERL_B200_CHECK_INDICES", "0") not in ("", "0")
 
 
@@ -575,6 +577,10 @@ def _run_categorical(a2c, logits, values, actions, old_log_prob, advantages, val
     _need(actions is not None, f"{who}: actions missing")
     _dense(actions, "actions", (torch.int64,))
     _need(actions.numel() == nb, f"{who}: one action index per sample")
+    if CHECK_INDICES and nb:   # the kernel maps an out-of-range action to 0 (memory safety only)
+      lo, hi = int(actions.min()), int(actions.max())
+      if lo < 0 or hi >= nact:
+        raise IndexError(f"{who}: action index out of range: [{lo}, {hi}] not within [0, {nact})")
   _check_value_side(who, nb, values, value_targets, old_values, a2c)
   lib, loss, stats, ws, ws_bytes = _loss_buffers(ref, nb)
   dlogits, dvalues = _grad_like(logits, ref), _grad_like(values, ref)
