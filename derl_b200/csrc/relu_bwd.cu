@@ -87,6 +87,7 @@ relu_bwd_bias_kernel(const T* __restrict__ grad_out, const T* __restrict__ out,
   const V* o = reinterpret_cast<const V*>(out);
   V* p = reinterpret_cast<V*>(grad_pre);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4   // four iterations' loads in flight per thread (the pointers are __restrict__)
   for (long long r = (long long)blockIdx.x * rpb + threadIdx.x / quads; r < rows;
        r += (long long)gridDim.x * rpb) {
     const long long at = r * quads + quad;
