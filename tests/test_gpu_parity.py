@@ -1352,13 +1352,16 @@ def test_fused_mlp_update_matches_the_reference_golden_update(golden):
   assert all(p.grad is None for p in model.parameters())
 
 
-@pytest.mark.parametrize("size,nmb,epochs,obs_dim,act_dim,obs_dtype", [
-    (384, 4, 2, 17, 6, np.float64),    # 96-row minibatches: a full and a partial 64-row pass
-    (100, 3, 2, 11, 3, np.float32),    # ragged: 33, 33, 33, 1
-    (2048, 32, 2, 26, 8, np.float64),  # BASELINE configs[1] minibatch shape, pybullet-sized obs
+@pytest.mark.parametrize("size,nmb,epochs,obs_dim,act_dim,obs_dtype,hp,clip_norm", [
+    (384, 4, 2, 17, 6, np.float64, None, .5),    # 96-row minibatches: a full and a partial 64-row pass
+    (100, 3, 2, 11, 3, np.float32, None, .5),    # ragged: 33, 33, 33, 1
+    (2048, 32, 2, 26, 8, np.float64, None, .5),  # BASELINE configs[1] minibatch shape, pybullet-sized obs
+    # no clipping anywhere (cliprange=None drops both clips, alg/ppo.py:47,83; no clip_grad_norm_)
+    # and an entropy bonus
+    (256, 4, 2, 17, 6, np.float64, dict(cliprange=None, value_loss_coef=.5, entropy_coef=.01), None),
 ])
 def test_fused_mlp_update_equals_the_per_minibatch_path(size, nmb, epochs, obs_dim, act_dim,
-                                                        obs_dtype):
+                                                        obs_dtype, hp, clip_norm):
   """Same seeds, same rollout: `PPO.learn()` on the fused kernel vs minibatch-by-minibatch
   `alg.step` (gather kernels + library MLP + K3 + torch clip/Adam).  The two are float32
   evaluations of the same formulas in different summation orders: the first loss (identical
@@ -1373,7 +1376,8 @@ def test_fused_mlp_update_equals_the_per_minibatch_path(size, nmb, epochs, obs_d
                  state=dict(latest_observations=rng.standard_normal(obs_dim).astype(obs_dtype)))
   results = []
   for fused in (True, False):
-    alg, model, _ = _mujoco_alg([rollout], obs_dim, act_dim, epochs, nmb)
+    alg, model, _ = _mujoco_alg([rollout], obs_dim, act_dim, epochs, nmb, hp=hp,
+                                max_grad_norm=clip_norm)
     np.random.seed(3)
     if fused:
       alg.learn(progress=False)
