@@ -64,11 +64,6 @@ static_assert(TcSmem::alloc <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kIdesc = umma_idesc_i8(128, 64, /*a u8*/ 0, /*b s8*/ 1, 0, 0);
 
-__device__ __forceinline__ void tma_store_2d_f(const void* tmap, const void* smem_src, int c0,
-                                               int c1) {
-  tma_store_2d(tmap, smem_src, c0, c1);
-}
-
 template <bool kMask>   // kMask: also emit the ReLU mask words (K7t's input)
 __global__ void __launch_bounds__(kThreads, 1)
 stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
@@ -268,8 +263,8 @@ stem_conv_relu_tc_kernel(const __grid_constant__ CUtensorMap tm_frames,
       fence_proxy_async_smem();              // staging writes -> visible to the TMA store
       named_bar_sync(1 + g, kEpiWarps * 32);
       if (gt == 0) {
-        tma_store_2d_f(&tm_out, stage, 0, (int)(f * 400));
-        tma_store_2d_f(&tm_out, stage + 200 * 128, 0, (int)(f * 400 + 200));
+        tma_store_2d(&tm_out, stage, 0, (int)(f * 400));
+        tma_store_2d(&tm_out, stage + 200 * 128, 0, (int)(f * 400 + 200));
         bulk_commit();
       }
       ++mine;
