@@ -163,7 +163,17 @@ int launch(const void* grad_out, const void* out, void* grad_pre, float* bias_gr
   const int quads = channels / 4;
   const int rpb = kThreads / quads;
   long long blocks = (rows + rpb - 1) / rpb;
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  // exactly one resident wave: the grid-stride loop balances itself, a partial second wave (8 CTAs
+  // per SM requested, 5 resident at 46 registers) left a 20-40 % tail
+  int resident = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, relu_bwd_bias_kernel<T>, kThreads,
+                                                    0) != cudaSuccess || resident < 1) {
+    cudaGetLastError();
+    resident = 4;
+  }
+  long long wave = (long long)sm_count() * resident;
+  if (wave > kMaxBlocks) wave = kMaxBlocks;
+  if (blocks > wave) blocks = wave;
   unsigned* ticket = reinterpret_cast<unsigned*>(workspace);
   float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kTicketBytes);
   DERL_CUDA(cudaMemsetAsync(workspace, 0, kTicketBytes, st));
