@@ -20,6 +20,21 @@ MIN_BYTES = 256 << 20     # smaller columns are simply uploaded
 MIN_ROW_BYTES = 2048      # TMA bulk path of the gather kernel
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+  """ONE high-priority upload stream per device, shared by every HostColumn: the caching
+  allocator pools freed blocks per stream, so a fresh stream per rollout would have to
+  cudaMalloc its multi-GB minibatch buffers again every time (a host-blocking call that used to
+  delay the first uploads of every rollout by 50-100 ms: `tools/trace_e2e.py`)."""
+  index = device.index if device.index is not None else torch.cuda.current_device()
+  stream = _SIDE_STREAMS.get(index)
+  if stream is None:
+    stream = _SIDE_STREAMS[index] = torch.cuda.Stream(torch.device("cuda", index), priority=-1)
+  return stream
+
+
 def eligible(array):
   """NumPy array -> pinned CPU tensor view if `array` qualifies for lazy upload, else None."""
   if not isinstance(array, np.ndarray) or array.ndim < 2 or not array.flags.c_contiguous:
@@ -98,7 +113,7 @@ class HostColumn:
     main = torch.cuda.current_stream(self.device)
     if self._stream is None:
       self._ensure_resident()
-      self._stream = torch.cuda.Stream(self.device, priority=-1)
+      self._stream = _side_stream(self.device)
       self._stream.wait_stream(main)        # resident allocation / anything before the rollout
     if ahead is not None:
       rows, done = ahead[1], ahead[2]

@@ -140,8 +140,14 @@ class IterateWithMinibatches(RunnerWrapper):
 
   @staticmethod
   def _upload(order, device):
+    # staged through pinned memory: a pageable copy would block the host until the stream has
+    # drained, once per epoch (the pinned block is recycled by the host allocator after the copy)
     host = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64))
-    return host.to(device, non_blocking=False)
+    if torch.device(device).type != "cuda":
+      return host.to(device)
+    pinned = torch.empty(host.shape, dtype=torch.int64, pin_memory=True)
+    pinned.copy_(host)
+    return pinned.to(device, non_blocking=True)
 
   @staticmethod
   def shuffle_interactions(interactions):
