@@ -3,7 +3,7 @@ the resident `value` and `e2e` go.  CUDA events are recorded on the side stream 
 upload+gather launch of `HostColumn` and on the main stream around every `alg.step`; all times are
 printed relative to the start of the traced step, with the host-side time of the same moments.
 
-    python tools/trace_e2e.py [--steps 2] [bench.py workload flags]
+    python tools/trace_e2e.py [--steps 2] [--upload-ctas 8] [bench.py workload flags]
 """
 import os
 import sys
@@ -17,10 +17,14 @@ import bench  # noqa: E402
 
 
 def main():
-  steps = 2
+  steps, upload_ctas = 2, None
   if "--steps" in sys.argv:
     i = sys.argv.index("--steps")
     steps = int(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
+  if "--upload-ctas" in sys.argv:   # CTAs of the upload+gather kernel (HostColumn default: 8)
+    i = sys.argv.index("--upload-ctas")
+    upload_ctas = int(sys.argv[i + 1])
     del sys.argv[i:i + 2]
   sys.argv = sys.argv[:1] + ["--steps", "1", "--warmup", "1"] + sys.argv[1:]
   args = bench.parse_args()
@@ -49,6 +53,8 @@ def main():
   issue = host_column.HostColumn._issue
 
   def traced_issue(self, perm, start, count):
+    if upload_ctas is not None:
+      self.max_ctas = upload_ctas
     with torch.cuda.stream(self._stream):
       s = torch.cuda.Event(enable_timing=True)
       s.record()
