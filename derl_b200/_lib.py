@@ -8,7 +8,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libderl_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 GAE_AUTO, GAE_DIRECT, GAE_TMA = 0, 1, 2
 GAE_STATS = 3
@@ -50,6 +50,10 @@ SIGNATURES = {
     "derl_b200_relu_bwd_bias_workspace_bytes": (_size, [_i64]),
     "derl_b200_relu_bwd_bias": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _int, _i64, _i64,
                                        _ptr, _size, _ptr]),
+    "derl_b200_linear_heads_workspace_bytes": (_size, [_int]),
+    "derl_b200_linear_heads_forward": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _ptr]),
+    "derl_b200_linear_heads_backward": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
+                                               _int, _int, _ptr, _size, _ptr]),
     "derl_b200_stem_conv_relu": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _int, _int, _ptr]),
     "derl_b200_space_to_depth": (_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "derl_b200_stem_backward_workspace_bytes": (_size, []),

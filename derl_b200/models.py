@@ -189,6 +189,8 @@ class NatureCNNBase(nn.Sequential):
   space_to_depth_hidden = True   # ... also for strided convs after the stem (the 4x4/2 layer):
                                  # avoids cuDNN's strided dgrad + layout folds (-5 % per update)
   fused_conv_relu = True
+  defer_linear_bias = False   # set by NatureCNNModel around its call: see `deferred_bias`
+  deferred_bias = None
 
   @staticmethod
   def _s2d_weight(conv):
@@ -286,6 +288,11 @@ class NatureCNNBase(nn.Sequential):
       weight = linear.weight.view(-1, chans, height, width).permute(0, 2, 3, 1).reshape(
           linear.out_features, -1)
       flat = hidden.permute(0, 2, 3, 1).reshape(batch, -1)
+      if self.defer_linear_bias and linear.bias is not None and flat.dtype == linear.bias.dtype:
+        # the caller (NatureCNNModel with fused heads, K9) adds the bias inside its own kernel and
+        # gets its gradient from the heads' column sums instead of a [B, 512] reduction
+        self.deferred_bias = linear.bias
+        return nn.functional.linear(flat, weight.to(flat.dtype), None)
       return nn.functional.linear(flat, weight.to(flat.dtype), linear.bias.to(flat.dtype)
                                   if linear.bias is not None else None)
     for layer in layers:                        # flatten, linear
@@ -329,11 +336,47 @@ class NatureCNNModel(nn.Module):
     if next(self.parameters()).is_cuda:
       self.to(memory_format=torch.channels_last)
 
+  fused_heads = True  # all output layers as ONE derl_b200 kernel over the 512 features (K9)
+
+  def _heads_fusable(self):
+    layers = list(self.output_layers)
+    return (self.fused_heads and self.autocast_dtype is None
+            and not torch.is_autocast_enabled("cuda")
+            and all(type(l) is nn.Linear and l.bias is not None and l.in_features == 512
+                    and l.weight.is_cuda and l.weight.dtype == torch.float32 for l in layers)
+            and 1 <= sum(l.out_features for l in layers) <= 32)
+
+  def _fused_heads(self, observations):
+    """Trunk with its last bias deferred, then every head in one kernel (K9)."""
+    base = self.base
+    base.defer_linear_bias, base.deferred_bias = True, None
+    try:
+      hidden = base(observations)
+      hidden_bias = base.deferred_bias
+    finally:
+      base.defer_linear_bias, base.deferred_bias = False, None
+    layers = list(self.output_layers)
+    if not (hidden.is_cuda and hidden.dtype == torch.float32 and hidden.dim() == 2
+            and hidden.is_contiguous()):
+      if hidden_bias is not None:
+        hidden = hidden + hidden_bias
+      return [layer(hidden) for layer in layers]
+    from . import ops  # noqa: F401
+    weight = torch.cat([l.weight for l in layers], 0) if len(layers) > 1 else layers[0].weight
+    bias = torch.cat([l.bias for l in layers], 0) if len(layers) > 1 else layers[0].bias
+    out = torch.ops.derl_b200.linear_heads(hidden, hidden_bias, weight.contiguous(),
+                                           bias.contiguous())
+    if len(layers) == 1:
+      return [out]
+    return [o.contiguous() for o in torch.split(out, [l.out_features for l in layers], 1)]
+
   def _forward(self, observations):
     if self.autocast_dtype is not None:
       with torch.autocast("cuda", dtype=self.autocast_dtype):
         hidden = self.base(observations)
         outputs = [layer(hidden).float() for layer in self.output_layers]
+    elif self._heads_fusable():
+      outputs = self._fused_heads(observations)
     else:
       hidden = self.base(observations)
       outputs = [layer(hidden) for layer in self.output_layers]

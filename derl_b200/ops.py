@@ -525,6 +525,89 @@ def _(grad_out, out, unblock=1):
           out.new_empty(chans, dtype=torch.float32))
 
 
+# --------------------------------------------------------------------------- K9: linear heads
+@torch.library.custom_op("derl_b200::linear_heads", mutates_args=(), device_types="cuda")
+def linear_heads(hidden: Tensor, hidden_bias: Optional[Tensor], weight: Tensor,
+                 bias: Tensor) -> Tensor:
+  """out [B, U] = (hidden [B, 512] + hidden_bias [512]) @ weight [U, 512].T + bias [U]: the
+  stacked nn.Linear heads of the actor-critic network (derl/models.py:201-202) in one pass."""
+  _dense(hidden, "hidden", (torch.float32,))
+  _dense(weight, "weight", (torch.float32,))
+  _dense(bias, "bias", (torch.float32,))
+  _need(hidden.dim() == 2 and weight.dim() == 2 and hidden.shape[1] == weight.shape[1],
+        "hidden [B, F] and weight [U, F] expected")
+  _need(bias.shape == (weight.shape[0],), "bias must be [U]")
+  if hidden_bias is not None:
+    _dense(hidden_bias, "hidden_bias", (torch.float32,))
+    _need(hidden_bias.shape == (hidden.shape[1],), "hidden_bias must be [F]")
+  batch, features = hidden.shape
+  units = weight.shape[0]
+  out = torch.empty((batch, units), dtype=torch.float32, device=hidden.device)
+  with _device_of(hidden, "linear_heads"):
+    _lib.check(_lib.load().derl_b200_linear_heads_forward(
+        _p(hidden), _p(hidden_bias), _p(weight), _p(bias), _p(out), batch, features, units,
+        _stream(hidden)), "linear_heads")
+  return out
+
+
+@linear_heads.register_fake
+def _(hidden, hidden_bias, weight, bias):
+  return hidden.new_empty((hidden.shape[0], weight.shape[0]))
+
+
+@torch.library.custom_op("derl_b200::linear_heads_backward", mutates_args=(), device_types="cuda")
+def linear_heads_backward(hidden: Tensor, hidden_bias: Optional[Tensor], weight: Tensor,
+                          grad_out: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+  """(grad_hidden [B, 512], grad_weight [U, 512], grad_bias [U], grad_hidden_bias [512] or an
+  empty tensor when hidden_bias is None) of `linear_heads`."""
+  _dense(hidden, "hidden", (torch.float32,))
+  _dense(weight, "weight", (torch.float32,))
+  _dense(grad_out, "grad_out", (torch.float32,))
+  batch, features = hidden.shape
+  units = weight.shape[0]
+  _need(grad_out.shape == (batch, units), "grad_out must be [B, U]")
+  _need(batch >= 1, "linear_heads_backward needs at least one row")
+  if hidden_bias is not None:
+    _dense(hidden_bias, "hidden_bias", (torch.float32,))
+  grad_hidden = torch.empty_like(hidden)
+  grad_weight = torch.empty_like(weight)
+  grad_bias = torch.empty(units, dtype=torch.float32, device=hidden.device)
+  grad_hb = torch.empty(features if hidden_bias is not None else 0, dtype=torch.float32,
+                        device=hidden.device)
+  lib = _lib.load()
+  ws_bytes = lib.derl_b200_linear_heads_workspace_bytes(units)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=hidden.device)
+  with _device_of(hidden, "linear_heads_backward"):
+    _lib.check(lib.derl_b200_linear_heads_backward(
+        _p(hidden), _p(hidden_bias), _p(weight), _p(grad_out), _p(grad_hidden), _p(grad_weight),
+        _p(grad_bias), _p(grad_hb), batch, features, units, _p(ws), ws_bytes, _stream(hidden)),
+        "linear_heads_backward")
+  return grad_hidden, grad_weight, grad_bias, grad_hb
+
+
+@linear_heads_backward.register_fake
+def _(hidden, hidden_bias, weight, grad_out):
+  return (torch.empty_like(hidden), torch.empty_like(weight), weight.new_empty(weight.shape[0]),
+          weight.new_empty(hidden.shape[1] if hidden_bias is not None else 0))
+
+
+def _linear_heads_setup(ctx, inputs, output):
+  hidden, hidden_bias, weight, _ = inputs
+  ctx.save_for_backward(hidden, weight, *([] if hidden_bias is None else [hidden_bias]))
+  ctx.has_hidden_bias = hidden_bias is not None
+
+
+def _linear_heads_bw(ctx, grad_out):
+  hidden, weight, *rest = ctx.saved_tensors
+  hidden_bias = rest[0] if ctx.has_hidden_bias else None
+  grad_hidden, grad_weight, grad_bias, grad_hb = torch.ops.derl_b200.linear_heads_backward(
+      hidden, hidden_bias, weight, grad_out.contiguous())
+  return grad_hidden, (grad_hb if ctx.has_hidden_bias else None), grad_weight, grad_bias
+
+
+linear_heads.register_autograd(_linear_heads_bw, setup_context=_linear_heads_setup)
+
+
 # --------------------------------------------------------------------------- K3: PPO / A2C loss
 def _loss_buffers(ref, nb):
   lib = _lib.load()

@@ -31,7 +31,7 @@ extern "C" {
 /* 2: derl_b200_stem_conv_relu / derl_b200_stem_backward gained `rows_dev` (fused minibatch gather).
  * 3: derl_b200_ppo_mlp_update (whole PPO update of the MuJoCo-shaped actor-critic in one launch),
  *    derl_b200_stem_conv_relu_mask / derl_b200_stem_backward_masked (tcgen05 stem pair). */
-#define DERL_B200_ABI_VERSION 3
+#define DERL_B200_ABI_VERSION 4
 
 enum {
   DERL_OK = 0,
@@ -290,6 +290,34 @@ int derl_b200_relu_bwd_bias(const void* grad_out_dev, const void* out_dev, void*
                             float* bias_grad_dev, int64_t rows, int64_t channels, int dtype,
                             int unblock, int64_t blocked_height, int64_t blocked_width,
                             void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ K9: linear output heads
+ * The heads of the actor-critic network, stacked into one weight [units, 512] (units = sum of
+ * the output widths, <= 32; rows in head order), applied to the trunk's 512 features in one pass:
+ *     out[r, u] = (hidden[r, :] + hidden_bias) . weight[u, :] + bias[u]
+ * Replaces `outputs = [layer(base_outputs) for layer in self.output_layers]`
+ * (derl/models.py:201-202: one nn.Linear(512, n) per output, derl/models.py:189-192) and, in
+ * backward, their input-gradient GEMMs + add, weight-gradient GEMMs and bias reductions:
+ *     grad_hidden[r, :] = sum_u grad_out[r, u] weight[u, :]
+ *     grad_weight[u, :] = sum_r grad_out[r, u] (hidden[r, :] + hidden_bias)
+ *     grad_bias[u]      = sum_r grad_out[r, u]
+ *     grad_hidden_bias  = sum_u grad_bias[u] weight[u, :]
+ * hidden_bias (nullable, [512]) is the bias of the trunk's last nn.Linear(3136, 512)
+ * (derl/models.py:112-114) when the caller passes the bias-free product as `hidden`: its gradient
+ * then costs 512 x units flops instead of a reduction over [batch, 512].  float32 FMA arithmetic,
+ * deterministic (per-CTA partials summed in a fixed order).  features must be 512; all float
+ * tensors dense row-major and 16-byte aligned.
+ * workspace >= derl_b200_linear_heads_workspace_bytes(units). */
+size_t derl_b200_linear_heads_workspace_bytes(int units);
+int derl_b200_linear_heads_forward(const float* hidden_dev, const float* hidden_bias_dev,
+                                   const float* weight_dev, const float* bias_dev, float* out_dev,
+                                   int64_t batch, int features, int units, void* stream);
+int derl_b200_linear_heads_backward(const float* hidden_dev, const float* hidden_bias_dev,
+                                    const float* weight_dev, const float* grad_out_dev,
+                                    float* grad_hidden_dev, float* grad_weight_dev,
+                                    float* grad_bias_dev, float* grad_hidden_bias_dev,
+                                    int64_t batch, int features, int units, void* workspace_dev,
+                                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer entry points
  * Same operations on HOST arrays (what a NumPy caller such as the reference's

@@ -1549,3 +1549,75 @@ def test_model_routes_float32_stem_through_the_tcgen05_pair():
       models._StemConvReLU.tensor_memory = True
   for a, b in zip(*grads):
     assert (a - b).abs().max() <= 1e-6 * max(b.abs().max().item(), 1e-12) + 1e-12
+
+
+# ------------------------------------------------------------------------------ K9: linear heads
+@pytest.mark.parametrize("batch,units,with_hidden_bias", [
+    (1, 5, True), (7, 5, False), (1000, 5, True), (4099, 19, True), (300, 32, False), (64, 1, True)])
+def test_linear_heads_match_float64_linear_layers(batch, units, with_hidden_bias):
+  """K9 forward and backward against the same formulas in float64 (`F.linear` heads on
+  hidden + bias, derl/models.py:201-202): float32 FMA arithmetic, so 1e-5 of each tensor's scale;
+  twice the same launch is bit-identical (fixed summation order)."""
+  K = torch.ops.derl_b200
+  gen = torch.Generator(device=DEV).manual_seed(batch * 37 + units)
+  hidden = torch.randn(batch, 512, device=DEV, generator=gen)
+  hb = torch.randn(512, device=DEV, generator=gen) * .3 if with_hidden_bias else None
+  weight = torch.randn(units, 512, device=DEV, generator=gen) * .05
+  bias = torch.randn(units, device=DEV, generator=gen)
+  grad_out = torch.randn(batch, units, device=DEV, generator=gen)
+  leaves = [t.clone().requires_grad_() for t in (hidden, weight, bias)]
+  hb_leaf = hb.clone().requires_grad_() if hb is not None else None
+  out = K.linear_heads(leaves[0], hb_leaf, leaves[1], leaves[2])
+  out.backward(grad_out)
+  h64, w64, b64 = (t.double().requires_grad_() for t in (hidden, weight, bias))
+  hb64 = hb.double().requires_grad_() if hb is not None else None
+  want = torch.nn.functional.linear(h64 + hb64 if hb is not None else h64, w64, b64)
+  want.backward(grad_out.double())
+
+  def close(got, ref, what):
+    scale = ref.abs().max().item() + 1e-30
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * scale, what
+  close(out, want, "out")
+  close(leaves[0].grad, h64.grad, "grad_hidden")
+  close(leaves[1].grad, w64.grad, "grad_weight")
+  close(leaves[2].grad, b64.grad, "grad_bias")
+  if hb is not None:
+    close(hb_leaf.grad, hb64.grad, "grad_hidden_bias")
+  again = K.linear_heads_backward(hidden, hb, weight, grad_out)
+  once = K.linear_heads_backward(hidden, hb, weight, grad_out)
+  assert all(torch.equal(a, b) for a, b in zip(again, once))
+  assert torch.equal(K.linear_heads(hidden, hb, weight, bias), out.detach())
+
+
+def test_model_with_fused_heads_equals_the_library_heads():
+  """NatureCNNModel.fused_heads on/off (float32 library arithmetic, TF32 off): same outputs and
+  parameter gradients to 2e-5 of their scale — including the trunk's deferred linear bias, whose
+  gradient comes from the heads' column sums."""
+  frames = torch.randint(0, 256, (48, 84, 84, 4), dtype=torch.uint8, device=DEV)
+  saved = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  try:
+    results = []
+    for fused in (True, False):
+      torch.manual_seed(0)
+      model = d.NatureCNNModel([6, 1])
+      with torch.no_grad():   # orthogonal_init zeroes the biases: make them count
+        for p in model.parameters():
+          if p.dim() == 1:
+            p.copy_(torch.randn_like(p) * .1)
+      model.fused_heads = fused
+      logits, values = model(frames)
+      assert logits.shape == (48, 6) and values.shape == (48, 1)
+      assert logits.is_contiguous() and values.is_contiguous()
+      (logits.square().sum() + (values * torch.arange(48, device=DEV)[:, None]).sum()).backward()
+      results.append(([logits.detach(), values.detach()],
+                      {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (outs_a, grads_a), (outs_b, grads_b) = results
+    for a, b in zip(outs_a, outs_b):
+      assert (a - b).abs().max() <= 2e-5 * b.abs().max()
+    for name in grads_b:
+      a, b = grads_a[name], grads_b[name]
+      assert (a - b).abs().max() <= 2e-5 * b.abs().max() + 1e-12, name
+  finally:
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
