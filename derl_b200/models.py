@@ -291,7 +291,7 @@ class NatureCNNBase(nn.Sequential):
       if self.defer_linear_bias and linear.bias is not None and flat.dtype == linear.bias.dtype:
         # the caller (NatureCNNModel with fused heads, K9) adds the bias inside its own kernel and
         # gets its gradient from the heads' column sums instead of a [B, 512] reduction
-        self.deferred_bias = linear.bias
+        self.__dict__["deferred_bias"] = linear.bias   # not a second registration of the Parameter
         return nn.functional.linear(flat, weight.to(flat.dtype), None)
       return nn.functional.linear(flat, weight.to(flat.dtype), linear.bias.to(flat.dtype)
                                   if linear.bias is not None else None)
@@ -349,12 +349,12 @@ class NatureCNNModel(nn.Module):
   def _fused_heads(self, observations):
     """Trunk with its last bias deferred, then every head in one kernel (K9)."""
     base = self.base
-    base.defer_linear_bias, base.deferred_bias = True, None
+    base.__dict__.update(defer_linear_bias=True, deferred_bias=None)
     try:
       hidden = base(observations)
-      hidden_bias = base.deferred_bias
+      hidden_bias = base.__dict__["deferred_bias"]
     finally:
-      base.defer_linear_bias, base.deferred_bias = False, None
+      base.__dict__.update(defer_linear_bias=False, deferred_bias=None)
     layers = list(self.output_layers)
     if not (hidden.is_cuda and hidden.dtype == torch.float32 and hidden.dim() == 2
             and hidden.is_contiguous()):

@@ -340,3 +340,35 @@ def test_bench_reference_arm_generates_the_same_rollout_without_importing_the_pa
   # and the arm's CPU path runs on it (oracle port here unless the reference tree is present)
   sec, how = bench.cpu_update_seconds(kind, nenvs, 5, 1, 1, steps=1, warmup=0)
   assert sec > 0 and how in ("live", "port")
+
+
+def test_fused_heads_plumbing_defers_and_restores_the_trunk_bias():
+  """NatureCNNModel._fused_heads asks the trunk to leave its last bias out (K9 adds it inside the
+  heads kernel); off the GPU the same code path must add it back and use the nn.Linear heads.
+  The deferred bias is an nn.Parameter handed over without registering it a second time."""
+  import torch.nn as nn
+
+  class Trunk(nn.Module):
+    defer_linear_bias, deferred_bias = False, None
+
+    def __init__(self):
+      super().__init__()
+      self.linear = nn.Linear(12, 512)
+
+    def forward(self, x):
+      if self.defer_linear_bias:
+        self.__dict__["deferred_bias"] = self.linear.bias
+        return nn.functional.linear(x, self.linear.weight, None)
+      return self.linear(x)
+
+  torch.manual_seed(0)
+  model = d.NatureCNNModel([3, 1]).cpu()
+  model.base = Trunk()
+  x = torch.randn(5, 12)
+  want = [layer(model.base(x)) for layer in model.output_layers]
+  got = model._fused_heads(x)
+  assert model.base.defer_linear_bias is False and model.base.deferred_bias is None
+  assert [n for n, _ in model.base.named_parameters()] == ["linear.weight", "linear.bias"]
+  for a, b in zip(got, want):
+    np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=1e-5, atol=1e-6)
+  assert not model._heads_fusable()   # CPU parameters: the library heads
