@@ -51,7 +51,7 @@ def parse_args():
   p.add_argument("--epochs", type=int, default=4)
   p.add_argument("--minibatches", type=int, default=4)
   p.add_argument("--nactions", type=int, default=4)
-  p.add_argument("--micro-batch", type=int, default=32768)
+  p.add_argument("--micro-batch", type=int, default=65536)   # rows per forward/backward pass
   p.add_argument("--net", choices=("tf32", "fp32", "bf16"), default="tf32",
                  help="tensor-core mode of the cuDNN/cuBLAS policy network (parameters fp32)")
   p.add_argument("--cpu-envs", type=int, default=32,
@@ -763,7 +763,7 @@ def run_ours(args, rank, world, local):
              "ms_per_step": sec_f / alt_steps * 1e3, "steps": alt_steps}
 
   # ---- informational: the same update as CUDA graphs (GraphedTrainer with micro-batches: one
-  # graph per 32768-row chunk + one update graph; frames reach the stem kernels by index)
+  # graph per micro-batch chunk + one update graph; frames reach the stem kernels by index)
   graphed = None
   if not args.no_alt and args.net == "tf32":
     alg_g, runner_g = build_alg(args, d, source, world, device, graphed=True)
