@@ -730,14 +730,18 @@ def run_ours(args, rank, world, local):
   if args.net != "fp32" and not args.no_alt:
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    # cuDNN's float32 engines are faster at 32768-row passes (0.47 vs 0.37 M samples/s at 65536)
+    micro_fp32 = min(args.micro_batch, 32768)
+    alg.trainer.micro_batch = micro_fp32
     sec_p, losses_p = timed_updates(alg, runner, nbatches, alt_steps, 2, world, False)
+    alg.trainer.micro_batch = args.micro_batch
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
     alt_fp32 = {"network": "fp32 (allow_tf32 off: cuDNN/cuBLAS float32, no INT8 stem kernels)",
                 "dtype": "f32; GAE f64 registers; u8 gather",
                 "value": samples_per_step * alt_steps / sec_p, "unit": "samples/s",
                 "ms_per_step": sec_p / alt_steps * 1e3, "steps": alt_steps, "warmup": 2,
-                "last_loss": float(losses_p[-1])}
+                "micro_batch": micro_fp32, "last_loss": float(losses_p[-1])}
 
   # ---- informational: the same update with the network under bf16 autocast
   alt = None
